@@ -1,0 +1,363 @@
+"""Host-side driver: one ``FeatureExtractor`` per parameter set and device.
+
+It owns a C-ABI plan (``hlmc_plan``) and exposes the batched calls the two
+preprocessing scripts use instead of their per-file librosa loops
+([R] src/1_preprocessing.py:223-258, src/1_preprocessing_advanced.py:286-314).
+torch is used only to own device memory and streams; numpy inputs go through
+the library's own pinned-host pipeline (``hlmc_extract_host``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import HlmcParams, lib
+
+STAT_NAMES = ("spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "zcr", "rms")
+
+
+class ParameterError(ValueError):
+    """Raised where librosa raises ``librosa.util.exceptions.ParameterError``."""
+
+
+class UnsupportedError(NotImplementedError):
+    """Valid for librosa but outside what the CUDA path implements."""
+
+
+def _check(rc: int):
+    if rc == _lib.HLMC_OK:
+        return
+    msg = _lib.last_error()
+    if rc == _lib.HLMC_ERR_PARAM:
+        raise ParameterError(msg)
+    if rc == _lib.HLMC_ERR_UNSUPPORTED:
+        raise UnsupportedError(msg)
+    raise RuntimeError(f"hlmc_b200: {msg} (status {rc})")
+
+
+def _resolve_window(window, win_length: int):
+    """librosa.filters.get_window: name / tuple / callable / array -> float64[win_length] or None (Hann)."""
+    if isinstance(window, str) and window in ("hann", "hanning"):
+        return None  # built into the C library (periodic Hann)
+    if callable(window):
+        w = np.asarray(window(win_length), dtype=np.float64)
+    elif isinstance(window, (str, tuple)) or np.isscalar(window):
+        import scipy.signal  # the same helper librosa delegates to
+
+        w = scipy.signal.get_window(window, win_length, fftbins=True).astype(np.float64)
+    else:
+        w = np.asarray(window, dtype=np.float64)
+    if w.shape != (win_length,):
+        raise ParameterError(f"Window size mismatch: {w.shape} != ({win_length},)")
+    return np.ascontiguousarray(w)
+
+
+def _ref_to_mode(ref):
+    if callable(ref):
+        if ref is np.max or ref is np.amax or ref is max:
+            return _lib.REF_MAX, 1.0
+        raise UnsupportedError("power_to_db: the only callable `ref` supported on device is np.max")
+    return _lib.REF_VALUE, float(abs(ref))
+
+
+class FeatureExtractor:
+    """Fused log-mel + MFCC + spectral statistics for batches of equal-length clips."""
+
+    def __init__(self, *, sr=22050, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                 center=True, pad_mode="constant", n_mels=128, fmin=0.0, fmax=None, htk=False,
+                 norm="slaney", power=2.0, n_mfcc=20, lifter=0, ref=1.0, amin=1e-10, top_db=80.0,
+                 roll_percent=0.85, zcr_threshold=1e-10, mel_basis=None, device=0):
+        if pad_mode not in _lib.PAD_MODES:
+            if pad_mode in ("wrap", "maximum", "mean", "median", "minimum"):
+                raise ParameterError(f"pad_mode='{pad_mode}' is not supported by librosa.stft")
+            raise UnsupportedError(f"pad_mode='{pad_mode}' is not implemented on device")
+        if norm not in ("slaney", None):
+            raise UnsupportedError("mel norm must be 'slaney' or None")
+        if top_db is not None and top_db < 0:
+            raise ParameterError("top_db must be non-negative")
+        if hop_length is None:
+            hop_length = int((win_length or n_fft) // 4)
+        p = HlmcParams()
+        lib.hlmc_params_default(C.byref(p))
+        p.sr, p.n_fft, p.hop_length = int(sr), int(n_fft), int(hop_length)
+        p.win_length = int(win_length) if win_length else int(n_fft)
+        p.center, p.pad_mode = int(bool(center)), _lib.PAD_MODES[pad_mode]
+        p.n_mels, p.fmin = int(n_mels), float(fmin)
+        p.fmax = float(fmax) if fmax is not None else -1.0
+        p.htk, p.mel_norm, p.power = int(bool(htk)), (1 if norm == "slaney" else 0), float(power)
+        p.n_mfcc, p.lifter = int(n_mfcc), float(lifter)
+        p.ref_mode, p.ref_value = _ref_to_mode(ref)
+        p.amin = float(amin)
+        p.top_db = float(top_db) if top_db is not None else -1.0
+        p.roll_percent, p.zcr_threshold = float(roll_percent), float(zcr_threshold)
+        self.params = p
+        self.device = int(device)
+        self._win = _resolve_window(window, p.win_length) if p.win_length > 0 else None
+        mb = None
+        if mel_basis is not None:
+            mb = np.ascontiguousarray(mel_basis, dtype=np.float32)
+            if mb.shape != (p.n_mels, 1 + p.n_fft // 2):
+                raise ParameterError("mel_basis shape mismatch")
+        self._mb = mb
+        handle = C.c_void_p()
+        _check(lib.hlmc_plan_create(
+            C.byref(p),
+            self._win.ctypes.data_as(C.c_void_p) if self._win is not None else None,
+            mb.ctypes.data_as(C.c_void_p) if mb is not None else None,
+            self.device, C.byref(handle)))
+        self._plan = handle
+        self._lock = threading.Lock()
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_plan", None):
+            lib.hlmc_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- introspection ------------------------------------------------------
+    @property
+    def n_mels(self):
+        return self.params.n_mels
+
+    @property
+    def n_mfcc(self):
+        return self.params.n_mfcc
+
+    @property
+    def n_bins(self):
+        return 1 + self.params.n_fft // 2
+
+    def num_frames(self, n: int) -> int:
+        t = lib.hlmc_num_frames(C.byref(self.params), int(n))
+        if t < 0:
+            _check(int(t))
+        return int(t)
+
+    def uses_fast_path(self) -> bool:
+        return bool(lib.hlmc_plan_uses_fast_path(self._plan))
+
+    def force_generic(self, flag: bool = True):
+        _check(lib.hlmc_plan_set_path(self._plan, int(bool(flag))))
+
+    def mel_basis(self) -> np.ndarray:
+        out = np.empty((self.n_mels, self.n_bins), dtype=np.float32)
+        _check(lib.hlmc_plan_mel_basis(self._plan, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dct_basis(self) -> np.ndarray:
+        out = np.empty((self.n_mfcc, self.n_mels), dtype=np.float32)
+        _check(lib.hlmc_plan_dct_basis(self._plan, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def pooled_width(self, with_mfcc=True) -> int:
+        return 2 * self.n_mels + (2 * self.n_mfcc if with_mfcc else 0) + 10
+
+    # -- device-resident path -----------------------------------------------
+    def _as_cuda_batch(self, waves):
+        import torch
+
+        if not (isinstance(waves, torch.Tensor) and waves.is_cuda):
+            raise TypeError("expected a CUDA torch.Tensor")
+        if waves.dtype != torch.float32:
+            raise ParameterError("Audio data must be float32")
+        if waves.dim() == 1:
+            waves = waves[None]
+        if waves.dim() != 2:
+            raise ParameterError("expected (B, n) waveforms")
+        if waves.stride(1) != 1:
+            waves = waves.contiguous()
+        if waves.device.index != self.device:
+            raise ParameterError(f"tensor is on cuda:{waves.device.index}, plan on cuda:{self.device}")
+        return waves
+
+    def extract_device(self, waves, *, mfcc=True, stats=True, status=True, pooled=False, out=None):
+        """(B, n) CUDA float32 -> dict of CUDA tensors; asynchronous on the current stream.
+
+        Keys: ``logmel`` (B, n_mels, T), ``mfcc`` (B, n_mfcc, T), ``stats`` (B, 5, T),
+        ``status`` (B,) int32, ``pooled`` (B, 2*n_mels + 2*n_mfcc + 10).  ``out`` may hold
+        preallocated tensors under the same keys (plus ``clipmax``).
+        """
+        import torch
+
+        waves = self._as_cuda_batch(waves)
+        B, n = waves.shape
+        T = self.num_frames(n)
+        dev = waves.device
+        out = dict(out) if out else {}
+        mfcc = bool(mfcc) and self.n_mfcc > 0
+
+        def buf(key, shape, dtype=torch.float32):
+            t = out.get(key)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous():
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                out[key] = t
+            return t
+
+        logmel = buf("logmel", (B, self.n_mels, T))
+        mf = buf("mfcc", (B, self.n_mfcc, T)) if mfcc else None
+        st = buf("stats", (B, 5, T)) if (stats or pooled) else None
+        sta = buf("status", (B,), torch.int32) if status else None
+        cm = buf("clipmax", (B,))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        _check(lib.hlmc_extract_device(self._plan, ptr(waves), B, n, waves.stride(0), ptr(logmel), ptr(mf),
+                                       ptr(st), ptr(sta), ptr(cm), C.c_void_p(stream)))
+        if pooled:
+            po = buf("pooled", (B, self.pooled_width(mfcc)))
+            _check(lib.hlmc_pool_device(self._plan, ptr(logmel), ptr(mf), ptr(st), B, T, ptr(po),
+                                        C.c_void_p(stream)))
+        return out
+
+    def melspectrogram_device(self, waves, *, stats=False):
+        import torch
+
+        waves = self._as_cuda_batch(waves)
+        B, n = waves.shape
+        T = self.num_frames(n)
+        mel = torch.empty((B, self.n_mels, T), dtype=torch.float32, device=waves.device)
+        st = torch.empty((B, 5, T), dtype=torch.float32, device=waves.device) if stats else None
+        stream = torch.cuda.current_stream(waves.device).cuda_stream
+        _check(lib.hlmc_melspectrogram_device(
+            self._plan, C.c_void_p(waves.data_ptr()), B, n, waves.stride(0), C.c_void_p(mel.data_ptr()),
+            C.c_void_p(st.data_ptr()) if st is not None else None, None, C.c_void_p(stream)))
+        return (mel, st) if stats else mel
+
+    def stats_device(self, waves):
+        """Only the five spectral / temporal statistics, (B, 5, T)."""
+        import torch
+
+        waves = self._as_cuda_batch(waves)
+        B, n = waves.shape
+        T = self.num_frames(n)
+        st = torch.empty((B, 5, T), dtype=torch.float32, device=waves.device)
+        stream = torch.cuda.current_stream(waves.device).cuda_stream
+        _check(lib.hlmc_melspectrogram_device(
+            self._plan, C.c_void_p(waves.data_ptr()), B, n, waves.stride(0), None,
+            C.c_void_p(st.data_ptr()), None, C.c_void_p(stream)))
+        return st
+
+    def stft_device(self, waves):
+        import torch
+
+        waves = self._as_cuda_batch(waves)
+        B, n = waves.shape
+        T = self.num_frames(n)
+        spec = torch.empty((B, self.n_bins, T, 2), dtype=torch.float32, device=waves.device)
+        stream = torch.cuda.current_stream(waves.device).cuda_stream
+        _check(lib.hlmc_stft_device(self._plan, C.c_void_p(waves.data_ptr()), B, n, waves.stride(0),
+                                    C.c_void_p(spec.data_ptr()), C.c_void_p(stream)))
+        return torch.view_as_complex(spec)
+
+    # -- host path (the reference-facing call) ---------------------------------
+    def extract_host(self, waves, *, logmel=True, mfcc=True, stats=True, status=True, pooled=False,
+                     chunk_clips=0, n_streams=3, out=None):
+        """(B, n) host float32 (numpy or CPU torch, ideally pinned) -> dict of numpy arrays.
+
+        H2D copies, kernels and D2H copies are overlapped inside the C library.
+        """
+        tensor_in = None
+        try:
+            import torch
+
+            if isinstance(waves, torch.Tensor):
+                if waves.is_cuda:
+                    raise TypeError("extract_host expects host memory; use extract_device")
+                tensor_in = waves
+                waves = waves.numpy()
+        except ImportError:  # pragma: no cover
+            pass
+        waves = np.asarray(waves)
+        if not np.issubdtype(waves.dtype, np.floating):
+            raise ParameterError("Audio data must be floating-point")
+        if waves.dtype != np.float32:
+            waves = waves.astype(np.float32)
+        if waves.ndim == 1:
+            waves = waves[None]
+        if waves.ndim != 2:
+            raise ParameterError("expected (B, n) waveforms")
+        if waves.strides[1] != 4 or waves.strides[0] % 4 or waves.strides[0] < 4 * waves.shape[1]:
+            waves = np.ascontiguousarray(waves)
+        B, n = waves.shape
+        T = self.num_frames(n)
+        mfcc = bool(mfcc) and self.n_mfcc > 0
+        out = dict(out) if out else {}
+
+        def buf(key, shape, dtype=np.float32):
+            a = out.get(key)
+            if a is None or a.shape != tuple(shape) or a.dtype != dtype or not a.flags.c_contiguous:
+                a = np.empty(shape, dtype=dtype)
+                out[key] = a
+            return a
+
+        lm = buf("logmel", (B, self.n_mels, T)) if logmel else None
+        mf = buf("mfcc", (B, self.n_mfcc, T)) if mfcc else None
+        st = buf("stats", (B, 5, T)) if stats else None
+        sta = buf("status", (B,), np.int32) if status else None
+        po = buf("pooled", (B, self.pooled_width(self.n_mfcc > 0))) if pooled else None
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        with self._lock:
+            _check(lib.hlmc_extract_host(self._plan, ptr(waves), B, n, waves.strides[0] // 4, ptr(lm),
+                                         ptr(mf), ptr(st), ptr(sta), ptr(po), int(chunk_clips),
+                                         int(n_streams)))
+        del tensor_in
+        return out
+
+    def last_transfer_bytes(self):
+        h2d, d2h = C.c_int64(0), C.c_int64(0)
+        lib.hlmc_last_transfer_bytes(self._plan, C.byref(h2d), C.byref(d2h))
+        return int(h2d.value), int(d2h.value)
+
+    def extract(self, waves, **kw):
+        """Dispatch on where ``waves`` lives."""
+        try:
+            import torch
+
+            if isinstance(waves, torch.Tensor) and waves.is_cuda:
+                return self.extract_device(waves, **kw)
+        except ImportError:  # pragma: no cover
+            pass
+        return self.extract_host(waves, **kw)
+
+
+_CACHE: dict = {}
+_CACHE_LOCK = threading.Lock()
+
+
+def get_extractor(**kw) -> FeatureExtractor:
+    """Process-wide plan cache keyed by the parameter set (plans are cheap but not free)."""
+    def freeze(v):
+        if isinstance(v, np.ndarray):
+            return ("nd", v.shape, v.tobytes())
+        if callable(v):
+            return ("fn", getattr(v, "__name__", repr(v)))
+        if isinstance(v, list):
+            return tuple(v)
+        return v
+
+    key = tuple(sorted((k, freeze(v)) for k, v in kw.items()))
+    with _CACHE_LOCK:
+        ex = _CACHE.get(key)
+        if ex is None:
+            ex = FeatureExtractor(**kw)
+            _CACHE[key] = ex
+        return ex
+
+
+def launch_count() -> int:
+    return int(lib.hlmc_launch_count())
+
+
+def measure_fp32_peak(device=0) -> float:
+    v = C.c_double(0.0)
+    _check(lib.hlmc_measure_fp32_peak(int(device), C.byref(v)))
+    return float(v.value)

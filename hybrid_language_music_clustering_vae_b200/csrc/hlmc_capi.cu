@@ -1,0 +1,554 @@
+// C ABI of the B200-native feature extractor: plan construction (host tables in
+// float64, rounded once), parameter validation with librosa's error behaviour,
+// the device entry points and the chunked host<->device pipeline.
+// Public contract: include/hlmc_b200.h.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hlmc_b200.h"
+#include "hlmc_internal.h"
+
+using namespace hlmc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return HLMC_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+    } while (0)
+
+struct HostPipeSlot {
+    cudaStream_t stream = nullptr;
+    float* d_wave = nullptr; float* d_logmel = nullptr; float* d_mfcc = nullptr;
+    float* d_stats = nullptr; float* d_pooled = nullptr; float* d_clipmax = nullptr;
+    int32_t* d_status = nullptr;
+};
+
+struct hlmc_plan {
+    hlmc_params p;
+    int device = 0, num_sms = 0, F = 0;
+    int force_generic = 0;
+    bool fast_ok = false;
+    std::vector<float> mel_dense, dct;           // host copies
+    int ncp = 0;
+    // device tables
+    float* d_fast = nullptr; FastTables ft{};
+    float* d_win = nullptr; float2* d_twm = nullptr; float2* d_tws = nullptr;
+    int* d_mel_lo = nullptr; int* d_mel_len = nullptr; int* d_mel_off = nullptr; float* d_mel_w = nullptr;
+    float* d_dct_t = nullptr;
+    // host pipeline
+    std::vector<HostPipeSlot> slots;
+    int64_t slot_chunk = 0, slot_n = 0; int slot_flags = 0;
+    int64_t last_h2d = 0, last_d2h = 0;
+};
+
+// ---------------------------------------------------------------------------
+// librosa.filters.mel restated in float64
+// ---------------------------------------------------------------------------
+static double hz_to_mel(double f, bool htk) {
+    if (htk) return 2595.0 * log10(1.0 + f / 700.0);
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = log(6.4) / 27.0;
+    if (f >= min_log_hz) return min_log_mel + log(f / min_log_hz) / logstep;
+    return f / f_sp;
+}
+static double mel_to_hz(double m, bool htk) {
+    if (htk) return 700.0 * (pow(10.0, m / 2595.0) - 1.0);
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = log(6.4) / 27.0;
+    if (m >= min_log_mel) return min_log_hz * exp(logstep * (m - min_log_mel));
+    return f_sp * m;
+}
+static void build_mel(const hlmc_params& p, std::vector<float>& w) {
+    const int F = p.n_fft / 2 + 1, nm = p.n_mels;
+    const double fmax = (p.fmax > 0.0f) ? double(p.fmax) : double(p.sr) / 2.0;
+    const double val = 1.0 / (double(p.n_fft) * (1.0 / double(p.sr)));   // np.fft.rfftfreq
+    std::vector<double> mel_f(nm + 2);
+    const double m0 = hz_to_mel(p.fmin, p.htk != 0), m1 = hz_to_mel(fmax, p.htk != 0);
+    const double step = (m1 - m0) / double(nm + 1);
+    for (int i = 0; i < nm + 2; ++i) mel_f[i] = mel_to_hz(i == nm + 1 ? m1 : m0 + i * step, p.htk != 0);
+    w.assign((size_t)nm * F, 0.0f);
+    for (int i = 0; i < nm; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = (p.mel_norm == HLMC_MELNORM_SLANEY) ? 2.0 / (mel_f[i + 2] - mel_f[i]) : 1.0;
+        for (int k = 0; k < F; ++k) {
+            const double fk = double(k) * val;
+            const double lower = -(mel_f[i] - fk) / fd0, upper = (mel_f[i + 2] - fk) / fd1;
+            double v = lower < upper ? lower : upper;
+            if (!(v > 0.0)) v = 0.0;
+            // librosa stores float32 weights, then scales the float32 array by float64 enorm
+            w[(size_t)i * F + k] = float(double(float(v)) * enorm);
+        }
+    }
+}
+
+static int validate(const hlmc_params& p) {
+    if (p.sr <= 0) return fail(HLMC_ERR_PARAM, "sr must be positive");
+    if (p.n_fft <= 0) return fail(HLMC_ERR_PARAM, "n_fft must be a positive integer");
+    if (p.hop_length <= 0) return fail(HLMC_ERR_PARAM, "hop_length must be a positive integer");
+    if (p.win_length <= 0 || p.win_length > p.n_fft)
+        return fail(HLMC_ERR_PARAM, "win_length must satisfy 0 < win_length <= n_fft (util.pad_center)");
+    if (p.n_fft < 64 || p.n_fft > 8192 || (p.n_fft & (p.n_fft - 1)))
+        return fail(HLMC_ERR_UNSUPPORTED, "n_fft must be a power of two in [64, 8192]");
+    if (p.pad_mode < 0 || p.pad_mode > 2) return fail(HLMC_ERR_PARAM, "unsupported pad_mode");
+    if (p.n_mels < 1 || p.n_mels > 32 * kMaxMelGroups) return fail(HLMC_ERR_UNSUPPORTED, "n_mels must be in [1, 256]");
+    if (p.n_mfcc < 0) return fail(HLMC_ERR_PARAM, "n_mfcc must be non-negative");
+    if (p.n_mfcc > p.n_mels || p.n_mfcc > 128) return fail(HLMC_ERR_UNSUPPORTED, "n_mfcc must be <= min(n_mels, 128)");
+    if (!(p.power == 1.0f || p.power == 2.0f)) return fail(HLMC_ERR_UNSUPPORTED, "power must be 1.0 or 2.0");
+    if (!(p.amin > 0.0f)) return fail(HLMC_ERR_PARAM, "amin must be strictly positive");
+    if (!(p.roll_percent > 0.0f && p.roll_percent < 1.0f)) return fail(HLMC_ERR_PARAM, "roll_percent must lie in the range (0, 1)");
+    if (p.lifter < 0.0f) return fail(HLMC_ERR_PARAM, "MFCC lifter must be a non-negative number");
+    if (p.fmin < 0.0f) return fail(HLMC_ERR_PARAM, "fmin must be non-negative");
+    if (p.zcr_threshold < 0.0f) return fail(HLMC_ERR_PARAM, "zero-crossing threshold must be non-negative");
+    if (p.ref_mode != HLMC_REF_VALUE && p.ref_mode != HLMC_REF_MAX) return fail(HLMC_ERR_PARAM, "bad ref_mode");
+    return HLMC_OK;
+}
+
+template <class T>
+static cudaError_t upload(T** dptr, const std::vector<T>& h) {
+    const size_t bytes = (h.empty() ? 1 : h.size()) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)dptr, bytes);
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+extern "C" {
+
+int hlmc_abi_version(void) { return HLMC_ABI_VERSION; }
+const char* hlmc_last_error(void) { return g_err.c_str(); }
+int64_t hlmc_launch_count(void) { return launch_count(); }
+
+void hlmc_params_default(hlmc_params* p) {
+    if (!p) return;
+    p->sr = 22050; p->n_fft = 2048; p->hop_length = 512; p->win_length = 2048;
+    p->center = 1; p->pad_mode = HLMC_PAD_CONSTANT;
+    p->n_mels = 128; p->fmin = 0.0f; p->fmax = -1.0f; p->htk = 0; p->mel_norm = HLMC_MELNORM_SLANEY;
+    p->power = 2.0f; p->n_mfcc = 20; p->lifter = 0.0f;
+    p->ref_mode = HLMC_REF_VALUE; p->ref_value = 1.0f; p->amin = 1e-10f; p->top_db = 80.0f;
+    p->roll_percent = 0.85f; p->zcr_threshold = 1e-10f;
+}
+
+int64_t hlmc_num_frames(const hlmc_params* p, int64_t n) {
+    if (!p || p->hop_length <= 0 || p->n_fft <= 0) return fail(HLMC_ERR_PARAM, "bad params");
+    if (n < 1) return fail(HLMC_ERR_PARAM, "Input is too short");
+    if (n > 0x3fffffff) return fail(HLMC_ERR_UNSUPPORTED, "clips longer than 2^30 samples are not supported");
+    if (p->center) return 1 + (n + 2 * (p->n_fft / 2) - p->n_fft) / p->hop_length;
+    if (n < p->n_fft) return fail(HLMC_ERR_PARAM, "n_fft is too large for uncentered analysis of this input");
+    return 1 + (n - p->n_fft) / p->hop_length;
+}
+
+void hlmc_plan_destroy(hlmc_plan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->device);
+    for (auto& s : plan->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(plan->d_fast); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
+    cudaFree(plan->d_mel_lo); cudaFree(plan->d_mel_len); cudaFree(plan->d_mel_off); cudaFree(plan->d_mel_w);
+    cudaFree(plan->d_dct_t);
+    delete plan;
+}
+
+int hlmc_plan_create(const hlmc_params* params, const double* window, const float* mel_basis,
+                     int device, hlmc_plan** out) {
+    if (!params || !out) return fail(HLMC_ERR_PARAM, "null argument");
+    *out = nullptr;
+    hlmc_params p = *params;
+    if (p.win_length <= 0) p.win_length = p.n_fft;
+    int rc = validate(p);
+    if (rc != HLMC_OK) return rc;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+        return fail(HLMC_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(HLMC_ERR_PARAM, "bad device ordinal");
+    CK(cudaSetDevice(device));
+
+    hlmc_plan* pl = new hlmc_plan();
+    pl->p = p; pl->device = device; pl->F = p.n_fft / 2 + 1;
+    cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
+    const char* fg = getenv("HLMC_FORCE_GENERIC");
+    pl->force_generic = (fg && fg[0] == '1') ? 1 : 0;
+    const int N = p.n_fft, M = N / 2, F = pl->F;
+
+    // window: scipy.signal.get_window(...) -> util.pad_center(size=n_fft); 0.5 folded in
+    std::vector<float> win(N, 0.0f);
+    {
+        const int lpad = (N - p.win_length) / 2;
+        for (int i = 0; i < p.win_length; ++i) {
+            const double w = window ? window[i] : 0.5 - 0.5 * cos(2.0 * M_PI * double(i) / double(p.win_length));
+            win[lpad + i] = float(0.5 * w);
+        }
+    }
+    // mel filterbank, dense then banded
+    if (mel_basis) pl->mel_dense.assign(mel_basis, mel_basis + (size_t)p.n_mels * F);
+    else build_mel(p, pl->mel_dense);
+    std::vector<int> lo(p.n_mels, 0), len(p.n_mels, 0), off(p.n_mels, 0);
+    std::vector<float> wpack;
+    for (int m = 0; m < p.n_mels; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < F; ++k)
+            if (pl->mel_dense[(size_t)m * F + k] != 0.0f) { if (first < 0) first = k; last = k; }
+        off[m] = (int)wpack.size();
+        if (first >= 0) {
+            lo[m] = first; len[m] = last - first + 1;
+            for (int k = first; k <= last; ++k) wpack.push_back(pl->mel_dense[(size_t)m * F + k]);
+        }
+    }
+    // DCT-II (scipy.fftpack.dct type=2 norm="ortho"), first n_mfcc rows, lifter folded in
+    const int nm = p.n_mels, nc = p.n_mfcc;
+    pl->dct.assign((size_t)nc * nm, 0.0f);
+    for (int c = 0; c < nc; ++c) {
+        const double s = (c == 0) ? sqrt(1.0 / nm) : sqrt(2.0 / nm);
+        // librosa.feature.mfcc lifter: M *= 1 + (lifter/2) * sin(pi * (c+1) / lifter)
+        const double lf = (p.lifter > 0.0f) ? 1.0 + (double(p.lifter) / 2.0) * sin(M_PI * double(c + 1) / double(p.lifter)) : 1.0;
+        for (int m = 0; m < nm; ++m)
+            pl->dct[(size_t)c * nm + m] = float(lf * s * cos(M_PI * double(c) * (2.0 * m + 1.0) / (2.0 * nm)));
+    }
+    const int ncps[7] = {8, 16, 24, 32, 40, 64, 128};
+    pl->ncp = 0;
+    for (int v : ncps) if (nc > 0 && v >= nc) { pl->ncp = v; break; }
+    std::vector<float> dct_t((size_t)nm * (pl->ncp > 0 ? pl->ncp : 1), 0.0f);
+    for (int c = 0; c < nc; ++c)
+        for (int m = 0; m < nm; ++m) dct_t[(size_t)m * pl->ncp + c] = pl->dct[(size_t)c * nm + m];
+
+    // generic-kernel tables
+    std::vector<float2> twm(M / 2), tws(M / 2 + 1);
+    for (int j = 0; j < M / 2; ++j) {
+        const double th = 2.0 * M_PI * double(j) / double(M);
+        twm[j] = make_float2(float(cos(th)), float(-sin(th)));
+    }
+    for (int k = 0; k <= M / 2; ++k) {
+        const double th = 2.0 * M_PI * double(k) / double(N);
+        tws[k] = make_float2(float(-sin(th)), float(-cos(th)));     // -i * W_N^k
+    }
+    cudaError_t e;
+#define UP(dst, vec) if ((e = upload(&pl->dst, vec)) != cudaSuccess) { hlmc_plan_destroy(pl); return cuda_fail(e, "upload " #dst); }
+    UP(d_win, win) UP(d_twm, twm) UP(d_tws, tws) UP(d_mel_lo, lo) UP(d_mel_len, len) UP(d_mel_off, off)
+    UP(d_mel_w, wpack) UP(d_dct_t, dct_t)
+
+    // fast-kernel table blob (n_fft == 2048 only)
+    if (N == kFastNfft) {
+        FastTables ft{};
+        const int ng = (nm + 31) / 32;
+        ft.n_groups = ng;
+        std::vector<int> meta(2 * kMaxMelGroups + 32 * ng, 0);
+        std::vector<float> melw;
+        int max_gmax = 0;
+        auto qof = [](int k) { return k + (k >> 4); };
+        for (int g = 0; g < ng; ++g) {
+            int gmax = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int m = 32 * g + l;
+                if (m < nm && len[m] > 0) {
+                    const int ql = qof(lo[m]), qh = qof(lo[m] + len[m] - 1);
+                    if (qh - ql + 1 > gmax) gmax = qh - ql + 1;
+                }
+            }
+            meta[g] = gmax;
+            meta[kMaxMelGroups + g] = (int)melw.size();
+            if (gmax > max_gmax) max_gmax = gmax;
+            const size_t base = melw.size();
+            melw.resize(base + (size_t)32 * gmax, 0.0f);
+            for (int l = 0; l < 32; ++l) {
+                const int m = 32 * g + l;
+                if (m >= nm || len[m] == 0) { meta[2 * kMaxMelGroups + m] = 0; continue; }
+                const int ql = qof(lo[m]), qh = qof(lo[m] + len[m] - 1);
+                meta[2 * kMaxMelGroups + m] = ql;
+                for (int q = ql; q <= qh; ++q) {
+                    if (q % 17 == 16) continue;                     // pad slot
+                    const int k = q - q / 17;
+                    melw[base + (size_t)32 * (q - ql) + l] = pl->mel_dense[(size_t)m * F + k];
+                }
+            }
+        }
+        auto r4 = [](int x) { return (x + 3) & ~3; };
+        ft.win = 0;
+        ft.tw1 = ft.win + N;
+        ft.tw2 = ft.tw1 + 31 * 32 * 2;
+        ft.mel_meta = ft.tw2 + 16 * 32 * 2;
+        ft.mel_w = r4(ft.mel_meta + (int)meta.size());
+        ft.total = r4(ft.mel_w + (int)melw.size());
+        ft.scr = r4(1089 + max_gmax + 1);
+        std::vector<float> blob(ft.total, 0.0f);
+        memcpy(&blob[ft.win], win.data(), N * 4);
+        for (int k1 = 1; k1 < 32; ++k1)
+            for (int l = 0; l < 32; ++l) {
+                const double th = 2.0 * M_PI * double((l * k1) % 1024) / 1024.0;
+                blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 0] = float(cos(th));
+                blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 1] = float(-sin(th));
+            }
+        for (int i = 0; i < 16; ++i)
+            for (int l = 0; l < 32; ++l) {
+                const double th = 2.0 * M_PI * double(16 * l + i) / 2048.0;
+                blob[ft.tw2 + (i * 32 + l) * 2 + 0] = float(-sin(th));
+                blob[ft.tw2 + (i * 32 + l) * 2 + 1] = float(-cos(th));
+            }
+        memcpy(&blob[ft.mel_meta], meta.data(), meta.size() * 4);
+        if (!melw.empty()) memcpy(&blob[ft.mel_w], melw.data(), melw.size() * 4);
+        pl->ft = ft;
+        UP(d_fast, blob)
+        pl->fast_ok = fast_smem_bytes(ft, 8, N, p.hop_length, nm) <= 227 * 1024;
+    }
+#undef UP
+    *out = pl;
+    return HLMC_OK;
+}
+
+int hlmc_plan_set_path(hlmc_plan* plan, int generic) {
+    if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
+    plan->force_generic = generic ? 1 : 0;
+    return HLMC_OK;
+}
+int hlmc_plan_uses_fast_path(const hlmc_plan* plan) {
+    return (plan && plan->fast_ok && !plan->force_generic) ? 1 : 0;
+}
+
+int hlmc_plan_mel_basis(const hlmc_plan* plan, float* h_out) {
+    if (!plan || !h_out) return fail(HLMC_ERR_PARAM, "null argument");
+    memcpy(h_out, plan->mel_dense.data(), plan->mel_dense.size() * 4);
+    return HLMC_OK;
+}
+int hlmc_plan_dct_basis(const hlmc_plan* plan, float* h_out) {
+    if (!plan || !h_out) return fail(HLMC_ERR_PARAM, "null argument");
+    if (!plan->dct.empty()) memcpy(h_out, plan->dct.data(), plan->dct.size() * 4);
+    return HLMC_OK;
+}
+
+static int run_frames(hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, int64_t pitch, int T,
+                      float* d_mel, float* d_stats, int32_t* d_status, float* d_clipmax, float* d_spec,
+                      cudaStream_t st) {
+    FrameArgs a{};
+    a.wave = d_wave; a.pitch = pitch; a.B = (int)B; a.n = (int)n; a.T = T;
+    a.n_fft = pl->p.n_fft; a.hop = pl->p.hop_length; a.pad = pl->p.center ? pl->p.n_fft / 2 : 0;
+    a.pad_mode = pl->p.pad_mode; a.n_mels = pl->p.n_mels; a.use_mag = (pl->p.power == 1.0f) ? 1 : 0;
+    a.binhz = float(double(pl->p.sr) / double(pl->p.n_fft));
+    a.roll_percent = pl->p.roll_percent; a.zcr_thr = pl->p.zcr_threshold;
+    a.mel_out = d_mel; a.stats = d_stats; a.status = d_status;
+    a.clipmax = reinterpret_cast<unsigned int*>(d_clipmax); a.spec = d_spec;
+    if (d_clipmax) CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));
+    if (d_status) CK(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
+    if (pl->fast_ok && !pl->force_generic && d_spec == nullptr) {
+        CK(launch_frames_fast(a, pl->d_fast, pl->ft, pl->num_sms, st));
+    } else {
+        GenericTables gt{pl->d_win, pl->d_twm, pl->d_tws, pl->d_mel_lo, pl->d_mel_len, pl->d_mel_off, pl->d_mel_w};
+        CK(launch_frames_generic(a, gt, st));
+    }
+    return HLMC_OK;
+}
+
+static int check_batch(const hlmc_plan* pl, const void* wave, int64_t B, int64_t n, int64_t pitch, int64_t* T) {
+    if (!pl) return fail(HLMC_ERR_PARAM, "null plan");
+    if (B < 0) return fail(HLMC_ERR_PARAM, "negative batch");
+    if (B > 0 && !wave) return fail(HLMC_ERR_PARAM, "null waveform pointer");
+    if (pitch < n) return fail(HLMC_ERR_PARAM, "pitch < n");
+    if (B > 0x7fffffff) return fail(HLMC_ERR_UNSUPPORTED, "batch too large for one call");
+    const int64_t t = hlmc_num_frames(&pl->p, n);
+    if (t < 0) return (int)t;
+    *T = t;
+    return HLMC_OK;
+}
+
+int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                        float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
+                        float* d_clipmax, void* stream) {
+    int64_t T;
+    int rc = check_batch(plan, d_wave, B, n, pitch, &T);
+    if (rc != HLMC_OK) return rc;
+    if (B == 0) return HLMC_OK;
+    if (!d_logmel || !d_clipmax) return fail(HLMC_ERR_PARAM, "d_logmel and d_clipmax are required");
+    if (d_mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
+    CK(cudaSetDevice(plan->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_logmel, d_stats, d_status, d_clipmax, nullptr, st);
+    if (rc != HLMC_OK) return rc;
+    DbArgs d{};
+    d.mel = d_logmel; d.mfcc = d_mfcc; d.clipmax = reinterpret_cast<const unsigned int*>(d_clipmax);
+    d.dct_t = plan->d_dct_t; d.B = (int)B; d.n_mels = plan->p.n_mels; d.n_mfcc = plan->p.n_mfcc;
+    d.ncp = plan->ncp; d.T = (int)T; d.ref_mode = plan->p.ref_mode; d.ref_value = plan->p.ref_value;
+    d.amin = plan->p.amin; d.top_db = plan->p.top_db;
+    CK(launch_db_dct(d, st));
+    return HLMC_OK;
+}
+
+int hlmc_melspectrogram_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                               float* d_mel, float* d_stats, int32_t* d_status, void* stream) {
+    int64_t T;
+    int rc = check_batch(plan, d_wave, B, n, pitch, &T);
+    if (rc != HLMC_OK) return rc;
+    if (B == 0) return HLMC_OK;
+    CK(cudaSetDevice(plan->device));
+    return run_frames(plan, d_wave, B, n, pitch, (int)T, d_mel, d_stats, d_status, nullptr, nullptr,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int hlmc_stft_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                     float* d_spec, void* stream) {
+    int64_t T;
+    int rc = check_batch(plan, d_wave, B, n, pitch, &T);
+    if (rc != HLMC_OK) return rc;
+    if (B == 0) return HLMC_OK;
+    if (!d_spec) return fail(HLMC_ERR_PARAM, "null output");
+    CK(cudaSetDevice(plan->device));
+    return run_frames(plan, d_wave, B, n, pitch, (int)T, nullptr, nullptr, nullptr, nullptr, d_spec,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int hlmc_power_to_db_device(const float* d_in, float* d_out, int64_t B, int64_t rows, int64_t T,
+                            int32_t ref_mode, float ref_value, float amin, float top_db,
+                            float* d_clipmax, int device, void* stream) {
+    if (!(amin > 0.0f)) return fail(HLMC_ERR_PARAM, "amin must be strictly positive");
+    if (B < 0 || rows < 0 || T < 0) return fail(HLMC_ERR_PARAM, "negative shape");
+    if (B == 0 || rows * T == 0) return HLMC_OK;
+    if (!d_in || !d_out || !d_clipmax) return fail(HLMC_ERR_PARAM, "null argument");
+    CK(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));
+    CK(launch_rowmax(d_in, reinterpret_cast<unsigned int*>(d_clipmax), B, rows * T, st));
+    CK(launch_power_to_db(d_in, d_out, reinterpret_cast<const unsigned int*>(d_clipmax), B, rows * T,
+                          ref_mode, ref_value, amin, top_db, st));
+    return HLMC_OK;
+}
+
+int hlmc_pool_device(hlmc_plan* plan, const float* d_logmel, const float* d_mfcc, const float* d_stats,
+                     int64_t B, int64_t T, float* d_pooled, void* stream) {
+    if (!plan || !d_logmel || !d_stats || !d_pooled) return fail(HLMC_ERR_PARAM, "null argument");
+    if (B <= 0 || T <= 0) return HLMC_OK;
+    CK(cudaSetDevice(plan->device));
+    CK(launch_pool(d_logmel, d_mfcc, d_stats, B, plan->p.n_mels, plan->p.n_mfcc, (int)T, d_pooled,
+                   static_cast<cudaStream_t>(stream)));
+    return HLMC_OK;
+}
+
+int hlmc_fix_frames_device(const float* d_in, float* d_out, int64_t B, int64_t rows, int64_t T,
+                           int64_t fixed, int device, void* stream) {
+    if (!d_in || !d_out) return fail(HLMC_ERR_PARAM, "null argument");
+    if (B <= 0 || rows <= 0 || T <= 0 || fixed <= 0) return fail(HLMC_ERR_PARAM, "bad shape");
+    CK(cudaSetDevice(device));
+    CK(launch_fix_frames(d_in, d_out, B, (int)rows, (int)T, (int)fixed, static_cast<cudaStream_t>(stream)));
+    return HLMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host pipeline: chunk the batch; H2D | kernels | D2H overlap across streams.
+// ---------------------------------------------------------------------------
+static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, int64_t T, int flags) {
+    if ((int)pl->slots.size() == n_streams && pl->slot_chunk >= chunk && pl->slot_n == n &&
+        (pl->slot_flags & flags) == flags)
+        return HLMC_OK;
+    for (auto& s : pl->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    pl->slots.assign(n_streams, HostPipeSlot());
+    const int64_t dp = (n + 3) & ~int64_t(3);
+    const int nm = pl->p.n_mels, nc = pl->p.n_mfcc;
+    for (auto& s : pl->slots) {
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaMalloc((void**)&s.d_wave, (size_t)chunk * dp * 4));
+        CK(cudaMalloc((void**)&s.d_logmel, (size_t)chunk * nm * T * 4));
+        if (nc > 0) CK(cudaMalloc((void**)&s.d_mfcc, (size_t)chunk * nc * T * 4));
+        CK(cudaMalloc((void**)&s.d_stats, (size_t)chunk * 5 * T * 4));
+        CK(cudaMalloc((void**)&s.d_pooled, (size_t)chunk * (2 * nm + 2 * nc + 10) * 4));
+        CK(cudaMalloc((void**)&s.d_clipmax, (size_t)chunk * 4));
+        CK(cudaMalloc((void**)&s.d_status, (size_t)chunk * 4));
+    }
+    pl->slot_chunk = chunk; pl->slot_n = n; pl->slot_flags = flags;
+    return HLMC_OK;
+}
+
+int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n, int64_t h_pitch,
+                      float* h_logmel, float* h_mfcc, float* h_stats, int32_t* h_status, float* h_pooled,
+                      int64_t chunk_clips, int n_streams) {
+    int64_t T;
+    int rc = check_batch(plan, h_wave, B, n, h_pitch, &T);
+    if (rc != HLMC_OK) return rc;
+    plan->last_h2d = plan->last_d2h = 0;
+    if (B == 0) return HLMC_OK;
+    if (h_mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
+    CK(cudaSetDevice(plan->device));
+    if (n_streams <= 0) n_streams = 3;
+    if (n_streams > 8) n_streams = 8;
+    if (chunk_clips <= 0) {
+        chunk_clips = (int64_t(64) << 20) / (n * 4);
+        if (chunk_clips < 1) chunk_clips = 1;
+    }
+    if (chunk_clips > B) chunk_clips = B;
+    rc = ensure_slots(plan, n_streams, chunk_clips, n, T, 0);
+    if (rc != HLMC_OK) return rc;
+    const int64_t dp = (n + 3) & ~int64_t(3);
+    const int nm = plan->p.n_mels, nc = plan->p.n_mfcc;
+    const bool want_mfcc = (h_mfcc != nullptr) || (h_pooled != nullptr && nc > 0);
+    const int pooled_w = 2 * nm + 2 * (want_mfcc ? nc : 0) + 10;
+    int64_t done = 0;
+    for (int64_t i = 0; done < B; ++i) {
+        HostPipeSlot& s = plan->slots[i % n_streams];
+        const int64_t c = (B - done < chunk_clips) ? (B - done) : chunk_clips;
+        CK(cudaMemcpy2DAsync(s.d_wave, (size_t)dp * 4, h_wave + done * h_pitch, (size_t)h_pitch * 4,
+                             (size_t)n * 4, (size_t)c, cudaMemcpyHostToDevice, s.stream));
+        plan->last_h2d += c * n * 4;
+        rc = hlmc_extract_device(plan, s.d_wave, c, n, dp, s.d_logmel, want_mfcc ? s.d_mfcc : nullptr,
+                                 s.d_stats, s.d_status, s.d_clipmax, s.stream);
+        if (rc != HLMC_OK) return rc;
+        if (h_pooled) {
+            CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, c, nm, nc, (int)T,
+                           s.d_pooled, s.stream));
+            CK(cudaMemcpyAsync(h_pooled + done * pooled_w, s.d_pooled, (size_t)c * pooled_w * 4,
+                               cudaMemcpyDeviceToHost, s.stream));
+            plan->last_d2h += c * pooled_w * 4;
+        }
+        if (h_logmel) {
+            CK(cudaMemcpyAsync(h_logmel + done * nm * T, s.d_logmel, (size_t)c * nm * T * 4,
+                               cudaMemcpyDeviceToHost, s.stream));
+            plan->last_d2h += c * nm * T * 4;
+        }
+        if (h_mfcc) {
+            CK(cudaMemcpyAsync(h_mfcc + done * nc * T, s.d_mfcc, (size_t)c * nc * T * 4,
+                               cudaMemcpyDeviceToHost, s.stream));
+            plan->last_d2h += c * nc * T * 4;
+        }
+        if (h_stats) {
+            CK(cudaMemcpyAsync(h_stats + done * 5 * T, s.d_stats, (size_t)c * 5 * T * 4,
+                               cudaMemcpyDeviceToHost, s.stream));
+            plan->last_d2h += c * 5 * T * 4;
+        }
+        if (h_status) {
+            CK(cudaMemcpyAsync(h_status + done, s.d_status, (size_t)c * 4, cudaMemcpyDeviceToHost, s.stream));
+            plan->last_d2h += c * 4;
+        }
+        done += c;
+    }
+    for (auto& s : plan->slots) CK(cudaStreamSynchronize(s.stream));
+    return HLMC_OK;
+}
+
+void hlmc_last_transfer_bytes(const hlmc_plan* plan, int64_t* h2d, int64_t* d2h) {
+    if (h2d) *h2d = plan ? plan->last_h2d : 0;
+    if (d2h) *d2h = plan ? plan->last_d2h : 0;
+}
+
+int hlmc_measure_fp32_peak(int device, double* tflops) {
+    if (!tflops) return fail(HLMC_ERR_PARAM, "null argument");
+    CK(cudaSetDevice(device));
+    CK(measure_fp32_peak(tflops));
+    return HLMC_OK;
+}
+
+}  // extern "C"

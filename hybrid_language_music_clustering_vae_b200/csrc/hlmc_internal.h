@@ -1,0 +1,81 @@
+// Internal interface between the C ABI (hlmc_capi.cu) and the kernels
+// (hlmc_kernels.cu).  Not installed; the public contract is include/hlmc_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hlmc {
+
+constexpr int kMaxMelGroups = 8;     // n_mels <= 256
+constexpr int kFastNfft = 2048;      // the register-FFT path is specialised for this size
+
+// Layout (in floats) of the table blob the fast kernel stages into shared memory.
+struct FastTables {
+    int win;        // n_fft floats: 0.5 * window (the real-FFT split's 1/2 is folded in)
+    int tw1;        // 31*32 float2: W_1024^(lane*k1), k1 = 1..31
+    int tw2;        // 17*32 float2: -i * W_2048^(16*lane + i), i = 0..15; row 16 = bin 512
+    int mel_meta;   // int32: gmax[8], goff[8], qlo[32*n_groups]
+    int mel_w;      // floats: per group, [i][lane] weights (zero padded to gmax)
+    int total;      // floats, multiple of 4
+    int n_groups;
+    int scr;        // per-warp scratch floats (>= 1089 + max gmax, multiple of 4)
+};
+
+struct FrameArgs {
+    const float* wave;      // (B, pitch)
+    long long pitch;
+    int B, n, T;
+    int n_fft, hop, pad;    // pad = center ? n_fft/2 : 0
+    int pad_mode;
+    int n_mels;
+    int use_mag;            // mel of |X| (power == 1) instead of |X|^2
+    float binhz;            // sr / n_fft
+    float roll_percent;
+    float zcr_thr;
+    float* mel_out;         // (B, n_mels, T) mel power; may be NULL (stats only)
+    float* stats;           // (B, 5, T) or NULL
+    int* status;            // (B) or NULL
+    unsigned int* clipmax;  // (B) float bits, max of mel power; or NULL
+    float* spec;            // (B, F, T, 2) complex STFT (generic kernel only) or NULL
+};
+
+// Generic-kernel tables (global memory).
+struct GenericTables {
+    const float* win;       // n_fft floats, 0.5 * window
+    const float2* twm;      // M/2 entries: W_M^j
+    const float2* tws;      // M/2+1 entries: -i * W_{2M}^k
+    const int* mel_lo;      // n_mels
+    const int* mel_len;     // n_mels
+    const int* mel_off;     // n_mels
+    const float* mel_w;     // nnz
+};
+
+struct DbArgs {
+    float* mel;             // in: mel power, out: power_to_db   (B, n_mels, T)
+    float* mfcc;            // (B, n_mfcc, T) or NULL
+    const unsigned int* clipmax;
+    const float* dct_t;     // (n_mels, ncp) transposed, zero padded DCT matrix
+    int B, n_mels, n_mfcc, ncp, T;
+    int ref_mode; float ref_value, amin, top_db;
+};
+
+// launchers (all asynchronous on `stream`; return cudaError_t)
+cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
+                               int num_sms, cudaStream_t stream);
+cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, cudaStream_t stream);
+cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream);
+cudaError_t launch_rowmax(const float* in, unsigned int* clipmax, long long B, long long per_clip,
+                          cudaStream_t stream);
+cudaError_t launch_power_to_db(const float* in, float* out, const unsigned int* clipmax, long long B,
+                               long long per_clip, int ref_mode, float ref_value, float amin,
+                               float top_db, cudaStream_t stream);
+cudaError_t launch_pool(const float* logmel, const float* mfcc, const float* stats, long long B,
+                        int n_mels, int n_mfcc, int T, float* pooled, cudaStream_t stream);
+cudaError_t launch_fix_frames(const float* in, float* out, long long B, int rows, int T, int fixed,
+                              cudaStream_t stream);
+cudaError_t measure_fp32_peak(double* tflops);
+int fast_smem_bytes(const FastTables& ft, int nwarps, int n_fft, int hop, int n_mels);
+int pick_fast_warps(int T);
+long long launch_count();
+
+}  // namespace hlmc

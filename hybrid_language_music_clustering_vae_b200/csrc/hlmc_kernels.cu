@@ -1,0 +1,957 @@
+// Hand-written sm_100a kernels for the audio feature hot path.
+//
+//   frames_fast_2048   persistent, one warp per frame: TMA-bulk-staged waveform
+//                      -> pad + window -> 1024-point complex FFT in registers
+//                      (two 32-point passes, one shared-memory transpose)
+//                      -> real-FFT split -> |X|^2, |X| -> centroid / bandwidth /
+//                      rolloff in registers -> banded mel projection -> staged,
+//                      coalesced store of the mel-power tile + per-clip max;
+//                      ZCR and RMS from the same staged samples.
+//   frames_generic     same outputs for any power-of-two n_fft (shared-memory
+//                      radix-2 FFT); also the librosa.stft entry point.
+//   db_dct             power_to_db (ref=max / top_db per clip) fused with the
+//                      orthonormal DCT-II (MFCC).
+//   pool / fix_frames  the scripts' time pooling and crop / pad-with-min.
+//
+// librosa semantics follow SURVEY.md Appendix A; each kernel names the call it
+// replaces.  No cuFFT / cuBLAS / Thrust anywhere.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <atomic>
+
+#include "fft_inreg.cuh"
+#include "hlmc_internal.h"
+
+namespace hlmc {
+
+static std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, d));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// np.pad index maps (librosa.stft / rms pad_mode; zero_crossing_rate is always "edge").
+__device__ __forceinline__ int reflect_index(int s, int n) {
+    if (n == 1) return 0;
+    int period = 2 * (n - 1);
+    s %= period;
+    if (s < 0) s += period;
+    return (s < n) ? s : period - s;
+}
+__device__ __forceinline__ float sample_padded(const float* __restrict__ clip, int n, int s,
+                                               int pad_mode) {
+    if (s >= 0 && s < n) return __ldg(clip + s);
+    if (pad_mode == 0) return 0.0f;
+    if (pad_mode == 1) return __ldg(clip + reflect_index(s, n));
+    return __ldg(clip + min(max(s, 0), n - 1));
+}
+__device__ __forceinline__ float sample_edge(const float* __restrict__ clip, int n, int s) {
+    return __ldg(clip + min(max(s, 0), n - 1));
+}
+
+// ---------------------------------------------------------------------------
+// Fast path: n_fft = 2048, one warp per frame, FFT in registers.
+// ---------------------------------------------------------------------------
+constexpr int kHdrFloats = 8;        // 2 mbarriers (16 B) + tile max [2] + pad
+
+__host__ __device__ constexpr int pos32(int k) { return fftreg::fft_pos<32>(k); }
+
+struct FastSmemLayout {
+    int tables, seg, seg_cap, stage, stage_sz, sstage, sstage_sz, scratch, total;
+};
+__host__ __device__ inline FastSmemLayout fast_layout(const FastTables& ft, int nw, int hop,
+                                                       int n_mels) {
+    FastSmemLayout L;
+    L.tables = kHdrFloats;
+    L.seg = L.tables + ft.total;
+    L.seg_cap = ((nw - 1) * hop + kFastNfft + 4 + 3) & ~3;
+    L.stage = L.seg + 2 * L.seg_cap;
+    L.stage_sz = (n_mels * (nw + 1) + 3) & ~3;
+    L.sstage = L.stage + 2 * L.stage_sz;
+    L.sstage_sz = (5 * nw + 3) & ~3;
+    L.scratch = L.sstage + 2 * L.sstage_sz;
+    L.total = L.scratch + nw * ft.scr;
+    return L;
+}
+int fast_smem_bytes(const FastTables& ft, int nwarps, int n_fft, int hop, int n_mels) {
+    (void)n_fft;
+    return fast_layout(ft, nwarps, hop, n_mels).total * 4;
+}
+// Warps per CTA (= frames per tile): a multiple of 4 (one per SM sub-partition)
+// that wastes the fewest warp slots in the last tile of a clip.
+int pick_fast_warps(int T) {
+    int best = 16; double best_eff = -1.0;
+    const int cand[3] = {16, 12, 8};
+    for (int c : cand) {
+        int tiles = (T + c - 1) / c;
+        double eff = double(T) / double(tiles * c);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+    }
+    return best;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NT = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const FastSmemLayout L = fast_layout(ft, NW, a.hop, a.n_mels);
+
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+    int* tilemax = reinterpret_cast<int*>(smem + 4);
+    float* tab = smem + L.tables;
+    const float2* s_win = reinterpret_cast<const float2*>(tab + ft.win);
+    const float2* s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
+    const float2* s_tw2 = reinterpret_cast<const float2*>(tab + ft.tw2);
+    const int* s_meta = reinterpret_cast<const int*>(tab + ft.mel_meta);
+    const float* s_melw = tab + ft.mel_w;
+    float* sc = smem + L.scratch + warp * ft.scr;
+
+    // ---- one-time CTA setup: tables -> smem, zero scratch/staging, barriers
+    for (int i = tid; i < ft.total / 4; i += NT)
+        reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
+    for (int i = L.stage + tid; i < L.total; i += NT) smem[i] = 0.0f;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        tilemax[0] = 0;
+        tilemax[1] = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int tiles_per_clip = (a.T + NW - 1) / NW;
+    const long long items = (long long)a.B * tiles_per_clip;
+
+    // Producer: one thread stages the samples a tile of NW frames touches.
+    auto issue_tile = [&](long long item, int buf) {
+        const int b = (int)(item / tiles_per_clip);
+        const int t0 = (int)(item - (long long)b * tiles_per_clip) * NW;
+        const int nf = min(NW, a.T - t0);
+        const int s_lo = max(0, t0 * a.hop - a.pad);
+        const int s_hi = min(a.n, (t0 + nf - 1) * a.hop - a.pad + kFastNfft);
+        const int cnt = s_hi - s_lo;
+        float* dst = smem + L.seg + buf * L.seg_cap;
+        if (cnt <= 0) { mbar_arrive(&mbar[buf]); return; }
+        const float* src = a.wave + (long long)b * a.pitch + s_lo;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
+        const uintptr_t a0 = addr & ~uintptr_t(15);
+        const int shift = (int)((addr - a0) >> 2);
+        const int total = shift + cnt;
+        const int bulk = total & ~3;
+        const float* src0 = reinterpret_cast<const float*>(a0);
+        for (int i = bulk; i < total; ++i) dst[i] = __ldg(src0 + i);   // <= 3 tail floats
+        if (bulk > 0) {
+            mbar_arrive_expect_tx(&mbar[buf], (uint32_t)bulk * 4u);
+            tma_bulk_g2s(dst, src0, (uint32_t)bulk * 4u, &mbar[buf]);
+        } else {
+            mbar_arrive(&mbar[buf]);
+        }
+    };
+
+    long long it = blockIdx.x;
+    if (tid == 0 && it < items) issue_tile(it, 0);
+
+    const float nthr = -a.zcr_thr;
+
+    for (int k = 0; it < items; it += gridDim.x, ++k) {
+        const int buf = k & 1;
+        if (tid == 0 && it + gridDim.x < items) issue_tile(it + gridDim.x, buf ^ 1);
+
+        const int b = (int)(it / tiles_per_clip);
+        const int t0 = (int)(it - (long long)b * tiles_per_clip) * NW;
+        const int nf = min(NW, a.T - t0);
+        const int s_lo = max(0, t0 * a.hop - a.pad);
+        const float* clip = a.wave + (long long)b * a.pitch;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(clip + s_lo) & 15) >> 2);
+        const float* seg = smem + L.seg + buf * L.seg_cap;
+        float* stage = smem + L.stage + buf * L.stage_sz;
+        float* sstage = smem + L.sstage + buf * L.sstage_sz;
+
+        mbar_wait(&mbar[buf], (uint32_t)((k >> 1) & 1));
+
+        if (warp < nf) {
+            const int t = t0 + warp;
+            const int fs = t * a.hop - a.pad;          // first sample of the frame (clip coords)
+            const int off = fs - s_lo + shift;
+            const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
+
+            float vr[64], vi[64];
+            float ss = 0.0f;
+            unsigned za = 0u, zb = 0u;
+
+            // ---- phase 0: frame -> registers; window; RMS and ZCR partials
+            if (interior && !(off & 1)) {
+                const float2* xp = reinterpret_cast<const float2*>(seg + off);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 x = xp[lane + 32 * j];
+                    const float2 w = s_win[lane + 32 * j];
+                    ss = fmaf(x.x, x.x, ss);
+                    ss = fmaf(x.y, x.y, ss);
+                    za |= (x.x < nthr) ? (1u << j) : 0u;
+                    zb |= (x.y < nthr) ? (1u << j) : 0u;
+                    vr[j] = x.x * w.x;
+                    vi[j] = x.y * w.y;
+                }
+            } else {
+                // edge frame (or odd alignment): mapped loads straight from global
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int s = fs + 2 * (lane + 32 * j);
+                    const float x0 = sample_padded(clip, a.n, s, a.pad_mode);
+                    const float x1 = sample_padded(clip, a.n, s + 1, a.pad_mode);
+                    const float e0 = sample_edge(clip, a.n, s);
+                    const float e1 = sample_edge(clip, a.n, s + 1);
+                    const float2 w = s_win[lane + 32 * j];
+                    ss = fmaf(x0, x0, ss);
+                    ss = fmaf(x1, x1, ss);
+                    za |= (e0 < nthr) ? (1u << j) : 0u;
+                    zb |= (e1 < nthr) ? (1u << j) : 0u;
+                    vr[j] = x0 * w.x;
+                    vi[j] = x1 * w.y;
+                }
+            }
+            // zero crossings: pairs (2m,2m+1) in-lane, pairs (2m+1,2m+2) with the next lane
+            int zc;
+            {
+                unsigned zn = __shfl_sync(FULL, za, (lane + 1) & 31);
+                unsigned msk = FULL;
+                if (lane == 31) { zn >>= 1; msk = 0x7fffffffu; }
+                zc = __popc(za ^ zb) + __popc((zb ^ zn) & msk);
+                zc = warp_sum_i(zc);
+            }
+            ss = warp_sum(ss);
+
+            // ---- phase 1: 32-point FFT over n1 (this lane holds z[lane + 32*n1])
+            fftreg::fft_dif<32>(vr, vi);
+
+            // ---- phase 2: inter-pass twiddle W_1024^(lane*k1)
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) {
+                const float2 w = s_tw1[(k1 - 1) * 32 + lane];
+                const int p = pos32(k1);
+                const float xr = vr[p], xi = vi[p];
+                vr[p] = fmaf(xr, w.x, -(xi * w.y));
+                vi[p] = fmaf(xr, w.y, xi * w.x);
+            }
+
+            // ---- phase 3: 32x32 transpose through shared memory (re, then im)
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) sc[lane * 33 + k1] = vr[pos32(k1)];
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) vr[n2] = sc[n2 * 33 + lane];
+            __syncwarp();
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) sc[lane * 33 + k1] = vi[pos32(k1)];
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) vi[n2] = sc[n2 * 33 + lane];
+            __syncwarp();
+
+            // ---- phase 4: 32-point FFT over n2; lane = k1, bin k = k1 + 32*k2 at pos32(k2)
+            fftreg::fft_dif<32>(vr, vi);
+
+            // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) and their
+            //      mirrors 1024-k (XOR-swizzled buffer: conflict-free both ways)
+            const int hb = lane >> 4;
+            const int base_lo = (lane << 4) ^ lane;
+            const int base_hi0 = ((16 * (64 - lane)) & 1023) ^ ((64 - lane) & 31);
+            const int base_hi = ((63 - lane) << 4) ^ (31 - lane);
+            float e512r, e512i;
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2)
+                sc[32 * k2 + (lane ^ (((2 * k2) & 31) | hb))] = vr[pos32(k2)];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vr[i] = sc[base_lo ^ i];
+            vr[16] = sc[base_hi0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) vr[16 + i] = sc[base_hi ^ (16 - i)];
+            e512r = sc[512];
+            __syncwarp();
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2)
+                sc[32 * k2 + (lane ^ (((2 * k2) & 31) | hb))] = vi[pos32(k2)];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vi[i] = sc[base_lo ^ i];
+            vi[16] = sc[base_hi0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) vi[16 + i] = sc[base_hi ^ (16 - i)];
+            e512i = sc[512];
+            __syncwarp();
+
+            // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
+            float m0l = 0.f, m1l = 0.f, m2l = 0.f, m0h = 0.f, m1h = 0.f, m2h = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float2 w = s_tw2[i * 32 + lane];
+                const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
+                const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
+                const float tx = fmaf(w.x, dx, -(w.y * dy));
+                const float ty = fmaf(w.x, dy, w.y * dx);
+                const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
+                const float pk = fmaf(ar, ar, ai * ai);
+                const float pm = fmaf(br, br, bi * bi);
+                const float sk = sqrtf(pk), sm = sqrtf(pm);
+                vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
+                const float d = float(i) - 7.5f;
+                m0l += sk; m1l = fmaf(d, sk, m1l); m2l = fmaf(d * d, sk, m2l);
+                m0h += sm; m1h = fmaf(-d, sm, m1h); m2h = fmaf(d * d, sm, m2h);
+            }
+            // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
+            const float p512 = 4.0f * fmaf(e512r, e512r, e512i * e512i);
+            const float s512 = sqrtf(p512);
+
+            // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
+            const float kcl = 16.0f * lane + 7.5f;
+            const float kch = 1024.0f - 16.0f * lane - 7.5f;
+            float s0 = m0l + m0h;
+            float s1 = fmaf(kcl, m0l, m1l) + fmaf(kch, m0h, m1h);
+            if (lane == 31) { s0 += s512; s1 = fmaf(512.0f, s512, s1); }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;   // util.normalize tiny guard
+            const float cen = s1 / denom;                            // in bins
+            float q;
+            {
+                const float dl = kcl - cen, dh = kch - cen;
+                q = fmaf(dl * dl, m0l, fmaf(2.0f * dl, m1l, m2l)) +
+                    fmaf(dh * dh, m0h, fmaf(2.0f * dh, m1h, m2h));
+                if (lane == 31) { const float dm = 512.0f - cen; q = fmaf(dm * dm, s512, q); }
+                q = warp_sum(q);
+            }
+            const float bw = sqrtf(fmaxf(q, 0.0f) / denom);
+
+            // ---- rolloff (librosa.feature.spectral_rolloff): first bin whose cumulative
+            //      magnitude reaches roll_percent * total
+            int rbin;
+            {
+                float pl = m0l;                       // inclusive scan, ascending lanes
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float tv = __shfl_up_sync(FULL, pl, d);
+                    if (lane >= d) pl += tv;
+                }
+                float ph = m0h;                       // inclusive scan, descending lanes
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float tv = __shfl_down_sync(FULL, ph, d);
+                    if (lane + d < 32) ph += tv;
+                }
+                const float tot_lo = __shfl_sync(FULL, pl, 31);
+                const float tot_hi = __shfl_sync(FULL, ph, 0);
+                const float mid = tot_lo + s512;      // s512 is warp-uniform (same smem word)
+                const float thr = a.roll_percent * (mid + tot_hi);
+                const unsigned lo_mask = __ballot_sync(FULL, pl >= thr);
+                if (lo_mask) {
+                    const int tl = __ffs(lo_mask) - 1;
+                    float cum = pl - m0l;
+                    int cnt = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { cum += vi[i]; cnt += (cum < thr) ? 1 : 0; }
+                    rbin = __shfl_sync(FULL, 16 * lane + min(cnt, 15), tl);
+                } else if (mid >= thr) {
+                    rbin = 512;
+                } else {
+                    const unsigned hi_mask = __ballot_sync(FULL, mid + ph >= thr);
+                    if (hi_mask) {
+                        const int tl = 31 - __clz(hi_mask);
+                        float cum = mid + (ph - m0h);
+                        int cnt = 0;
+#pragma unroll
+                        for (int i = 15; i >= 0; --i) { cum += vi[16 + i]; cnt += (cum < thr) ? 1 : 0; }
+                        // ascending bins are i = 15..0: cnt-th of them is i = 15 - cnt
+                        rbin = __shfl_sync(FULL, 1024 - 16 * lane - (15 - min(cnt, 15)), tl);
+                    } else {
+                        rbin = 1024;
+                    }
+                }
+            }
+
+            // ---- phase 7: power (or magnitude) spectrum -> padded scratch, q(k) = k + k/16
+            if (a.use_mag) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vi[i];
+                sc[17 * (64 - lane)] = vi[16];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vi[16 + i];
+                if (lane == 31) sc[544] = s512;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vr[i];
+                sc[17 * (64 - lane)] = vr[16];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vr[16 + i];
+                if (lane == 31) sc[544] = p512;
+            }
+            sc[17 * lane + 16] = 0.0f;
+            sc[17 * (63 - lane) + 16] = 0.0f;
+            __syncwarp();
+
+            // ---- phase 8: banded mel projection (librosa.feature.melspectrogram's einsum)
+            float wmax = 0.0f;
+            if (a.mel_out != nullptr) {
+                for (int g = 0; g < ft.n_groups; ++g) {
+                    const int gmax = s_meta[g];
+                    const float* wp = s_melw + s_meta[kMaxMelGroups + g] + lane;
+                    const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * g + lane];
+                    float acc = 0.0f;
+#pragma unroll 4
+                    for (int i = 0; i < gmax; ++i) acc = fmaf(wp[32 * i], pp[i], acc);
+                    const int m = 32 * g + lane;
+                    if (m < a.n_mels) stage[m * (NW + 1) + warp] = acc;
+                    wmax = fmaxf(wmax, acc);
+                }
+                wmax = warp_max(wmax);
+            }
+            __syncwarp();   // scratch is reused by the next frame's transposes
+
+            if (lane == 0) {
+                sstage[0 * NW + warp] = cen * a.binhz;
+                sstage[1 * NW + warp] = bw * a.binhz;
+                sstage[2 * NW + warp] = float(rbin) * a.binhz;
+                sstage[3 * NW + warp] = float(zc) * (1.0f / float(kFastNfft));
+                sstage[4 * NW + warp] = sqrtf(ss * (1.0f / float(kFastNfft)));
+                if (a.mel_out != nullptr) atomicMax(&tilemax[buf], __float_as_int(wmax));
+                // librosa.util.valid_audio: a non-finite sample poisons the sum of squares
+                if (a.status != nullptr && !(fabsf(ss) <= 3.0e38f)) atomicOr(a.status + b, 1);
+            }
+        }
+        __syncthreads();
+
+        // ---- flush the tile: rows of nf consecutive frames per mel band
+        if (a.mel_out != nullptr) {
+            float* outb = a.mel_out + (size_t)b * a.n_mels * a.T + t0;
+            for (int idx = tid; idx < a.n_mels * NW; idx += NT) {
+                const int m = idx / NW, j = idx - m * NW;
+                if (j < nf) outb[(size_t)m * a.T + j] = stage[m * (NW + 1) + j];
+            }
+        }
+        if (a.stats != nullptr && tid < 5 * NW) {
+            const int s = tid / NW, j = tid - s * NW;
+            if (j < nf) a.stats[((size_t)b * 5 + s) * a.T + t0 + j] = sstage[s * NW + j];
+        }
+        if (tid == 0 && a.clipmax != nullptr) {
+            const int v = tilemax[buf];
+            tilemax[buf] = 0;
+            atomicMax(reinterpret_cast<int*>(a.clipmax) + b, v);
+        }
+    }
+}
+
+template <int NW>
+static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, const FastTables& ft,
+                                  int num_sms, cudaStream_t stream) {
+    const int smem = fast_smem_bytes(ft, NW, a.n_fft, a.hop, a.n_mels);
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (long long)a.B * ((a.T + NW - 1) / NW);
+    const int grid = (int)((items < num_sms) ? items : num_sms);
+    if (grid <= 0) return cudaSuccess;
+    frames_fast_2048<NW><<<grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
+                               int num_sms, cudaStream_t stream) {
+    int nw = pick_fast_warps(a.T);
+    // fall back to fewer warps if the shared-memory budget (227 KB) is exceeded
+    while (nw > 8 && fast_smem_bytes(ft, nw, a.n_fft, a.hop, a.n_mels) > 227 * 1024) nw -= 4;
+    if (fast_smem_bytes(ft, nw, a.n_fft, a.hop, a.n_mels) > 227 * 1024) return cudaErrorInvalidValue;
+    switch (nw) {
+        case 16: return launch_fast_nw<16>(a, d_tables, ft, num_sms, stream);
+        case 12: return launch_fast_nw<12>(a, d_tables, ft, num_sms, stream);
+        default: return launch_fast_nw<8>(a, d_tables, ft, num_sms, stream);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Generic path: any power-of-two n_fft, one warp per frame, FFT in shared memory.
+// Also serves librosa.stft (writes the complex spectrum when a.spec != NULL).
+// ---------------------------------------------------------------------------
+constexpr int kGenWarps = 4;
+
+__global__ void __launch_bounds__(kGenWarps * 32)
+frames_generic(const FrameArgs a, const GenericTables gt, int logM) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = a.n_fft >> 1, F = M + 1;
+    float2* Z = reinterpret_cast<float2*>(smem) + (size_t)warp * M;
+    float* Pb = smem + (size_t)kGenWarps * M * 2 + (size_t)warp * (F + 3);
+
+    const long long frame_id = (long long)blockIdx.x * kGenWarps + warp;
+    if (frame_id >= (long long)a.B * a.T) return;      // whole warp exits together
+    const int b = (int)(frame_id / a.T);
+    const int t = (int)(frame_id - (long long)b * a.T);
+    const float* clip = a.wave + (long long)b * a.pitch;
+    const int fs = t * a.hop - a.pad;
+
+    // ZCR (edge padded, librosa.feature.zero_crossing_rate) and RMS (pad_mode, feature.rms)
+    float ss = 0.0f;
+    int zc = 0;
+    unsigned prev_last = 0u;
+    for (int c = 0; c < a.n_fft / 32; ++c) {
+        const int s = fs + 32 * c + lane;
+        const float x = sample_padded(clip, a.n, s, a.pad_mode);
+        const float e = sample_edge(clip, a.n, s);
+        ss = fmaf(x, x, ss);
+        const unsigned msk = __ballot_sync(FULL, e < -a.zcr_thr);
+        zc += __popc((msk ^ (msk >> 1)) & 0x7fffffffu);
+        if (c > 0) zc += ((msk & 1u) != prev_last) ? 1 : 0;
+        prev_last = msk >> 31;
+    }
+    ss = warp_sum(ss);
+
+    // windowed frame packed as M complex points, bit-reversed for the DIT passes
+    for (int m = lane; m < M; m += 32) {
+        const float x0 = sample_padded(clip, a.n, fs + 2 * m, a.pad_mode);
+        const float x1 = sample_padded(clip, a.n, fs + 2 * m + 1, a.pad_mode);
+        const int r = (int)(__brev((unsigned)m) >> (32 - logM));
+        Z[r] = make_float2(x0 * gt.win[2 * m], x1 * gt.win[2 * m + 1]);
+    }
+    __syncwarp();
+    for (int s = 1; s <= logM; ++s) {
+        const int half = 1 << (s - 1);
+        const int tstride = M >> s;
+        for (int idx = lane; idx < M / 2; idx += 32) {
+            const int j = idx & (half - 1);
+            const int i0 = ((idx - j) << 1) + j, i1 = i0 + half;
+            const float2 w = gt.twm[j * tstride];
+            const float2 u = Z[i0], v = Z[i1];
+            const float tr = fmaf(v.x, w.x, -(v.y * w.y));
+            const float ti = fmaf(v.x, w.y, v.y * w.x);
+            Z[i0] = make_float2(u.x + tr, u.y + ti);
+            Z[i1] = make_float2(u.x - tr, u.y - ti);
+        }
+        __syncwarp();
+    }
+    // split into the 1 + n_fft/2 real-FFT bins; power and magnitude
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int k = lane; k <= M / 2; k += 32) {
+        const float2 za = Z[k], zb = Z[(M - k) & (M - 1)];
+        const float2 w = gt.tws[k];
+        const float ex = za.x + zb.x, ey = za.y - zb.y, dx = za.x - zb.x, dy = za.y + zb.y;
+        const float tx = fmaf(w.x, dx, -(w.y * dy)), ty = fmaf(w.x, dy, w.y * dx);
+        const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = -(ey - ty);
+        const float pk = fmaf(ar, ar, ai * ai), pm = fmaf(br, br, bi * bi);
+        Pb[k] = pk;
+        Pb[M - k] = pm;
+        if (a.spec != nullptr) {
+            float2* sp = reinterpret_cast<float2*>(a.spec) + (size_t)b * F * a.T + t;
+            sp[(size_t)k * a.T] = make_float2(ar, ai);
+            sp[(size_t)(M - k) * a.T] = make_float2(br, bi);
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < F; k += 32) {
+        const float s = sqrtf(Pb[k]);
+        s0 += s;
+        s1 = fmaf(float(k), s, s1);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;
+    const float cen = s1 / denom;
+    float q = 0.0f;
+    for (int k = lane; k < F; k += 32) {
+        const float d = float(k) - cen;
+        q = fmaf(d * d, sqrtf(Pb[k]), q);
+    }
+    q = warp_sum(q);
+    const float bw = sqrtf(q / denom);
+    // rolloff: row-by-row inclusive scan of the magnitudes
+    int rbin = F - 1;
+    {
+        const float thr = a.roll_percent * s0;
+        float run = 0.0f;
+        bool found = false;
+        for (int k0 = 0; k0 < F && !found; k0 += 32) {
+            const int k = k0 + lane;
+            float v = (k < F) ? sqrtf(Pb[k]) : 0.0f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float tv = __shfl_up_sync(FULL, v, d);
+                if (lane >= d) v += tv;
+            }
+            const unsigned msk = __ballot_sync(FULL, (k < F) && (run + v >= thr));
+            if (msk) { rbin = k0 + __ffs(msk) - 1; found = true; }
+            run += __shfl_sync(FULL, v, 31);
+        }
+    }
+    if (lane == 0) {
+        if (a.stats != nullptr) {
+            float* st = a.stats + (size_t)b * 5 * a.T + t;
+            st[0] = cen * a.binhz;
+            st[(size_t)a.T] = bw * a.binhz;
+            st[(size_t)2 * a.T] = float(rbin) * a.binhz;
+            st[(size_t)3 * a.T] = float(zc) / float(a.n_fft);
+            st[(size_t)4 * a.T] = sqrtf(ss / float(a.n_fft));
+        }
+        if (a.status != nullptr && !(fabsf(ss) <= 3.0e38f)) atomicOr(a.status + b, 1);
+    }
+    if (a.mel_out != nullptr) {
+        float wmax = 0.0f;
+        for (int m = lane; m < a.n_mels; m += 32) {
+            const int lo = gt.mel_lo[m], len = gt.mel_len[m];
+            const float* w = gt.mel_w + gt.mel_off[m];
+            float acc = 0.0f;
+            for (int i = 0; i < len; ++i) {
+                const float p = Pb[lo + i];
+                acc = fmaf(w[i], a.use_mag ? sqrtf(p) : p, acc);
+            }
+            a.mel_out[((size_t)b * a.n_mels + m) * a.T + t] = acc;
+            wmax = fmaxf(wmax, acc);
+        }
+        wmax = warp_max(wmax);
+        if (lane == 0 && a.clipmax != nullptr)
+            atomicMax(reinterpret_cast<int*>(a.clipmax) + b, __float_as_int(wmax));
+    }
+}
+
+cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, cudaStream_t stream) {
+    const int M = a.n_fft / 2;
+    int logM = 0;
+    while ((1 << logM) < M) ++logM;
+    const int smem = kGenWarps * (M * 8 + (M + 4) * 4);
+    cudaError_t e = cudaFuncSetAttribute(frames_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const long long frames = (long long)a.B * a.T;
+    if (frames <= 0) return cudaSuccess;
+    const long long grid = (frames + kGenWarps - 1) / kGenWarps;
+    frames_generic<<<(unsigned)grid, kGenWarps * 32, smem, stream>>>(a, gt, logM);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// power_to_db (per-clip ref=max / top_db) fused with the DCT-II of librosa.feature.mfcc.
+// One thread per (clip, frame); DCT matrix broadcast from shared memory.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float db10(float x) { return 3.0102999566398120f * __log2f(x); }
+
+template <int NC>
+__global__ void __launch_bounds__(128) db_dct(const DbArgs a) {
+    extern __shared__ __align__(16) float sD[];
+    if (NC > 0) {
+        for (int i = threadIdx.x; i < a.n_mels * NC; i += 128) sD[i] = a.dct_t[i];
+        __syncthreads();
+    }
+    const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (g >= (long long)a.B * a.T) return;
+    const int b = (int)(g / a.T), t = (int)(g - (long long)b * a.T);
+    const float pmax = __uint_as_float(a.clipmax[b]);
+    const float maxa = db10(fmaxf(a.amin, pmax));
+    const float ref_db = (a.ref_mode == 1) ? maxa : db10(fmaxf(a.amin, fabsf(a.ref_value)));
+    const float floor_db = (a.top_db >= 0.0f) ? (maxa - ref_db) - a.top_db : -CUDART_INF_F;
+    // librosa.feature.mfcc always calls power_to_db(S) with ref=1.0, amin=1e-10, top_db=80
+    const bool same_amin = (a.amin == 1e-10f);
+    const float floor_m = db10(fmaxf(1e-10f, pmax)) - 80.0f;
+    float acc[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0f;
+    float* col = a.mel + (size_t)b * a.n_mels * a.T + t;
+    for (int m = 0; m < a.n_mels; ++m) {
+        const float p = col[(size_t)m * a.T];
+        const float adb = db10(fmaxf(a.amin, p));
+        col[(size_t)m * a.T] = fmaxf(adb - ref_db, floor_db);
+        if (NC > 0) {
+            float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
+            x = fmaxf(x, floor_m);
+            const float4* d4 = reinterpret_cast<const float4*>(sD + m * NC);
+#pragma unroll
+            for (int c = 0; c < NC / 4; ++c) {
+                const float4 d = d4[c];
+                acc[4 * c + 0] = fmaf(d.x, x, acc[4 * c + 0]);
+                acc[4 * c + 1] = fmaf(d.y, x, acc[4 * c + 1]);
+                acc[4 * c + 2] = fmaf(d.z, x, acc[4 * c + 2]);
+                acc[4 * c + 3] = fmaf(d.w, x, acc[4 * c + 3]);
+            }
+        }
+    }
+    if (NC > 0) {
+        float* mo = a.mfcc + (size_t)b * a.n_mfcc * a.T + t;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (c < a.n_mfcc) mo[(size_t)c * a.T] = acc[c];
+    }
+}
+
+template <int NC>
+static cudaError_t launch_db_nc(const DbArgs& a, cudaStream_t stream) {
+    const long long frames = (long long)a.B * a.T;
+    if (frames <= 0) return cudaSuccess;
+    const int smem = a.n_mels * NC * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(db_dct<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    db_dct<NC><<<(unsigned)((frames + 127) / 128), 128, smem, stream>>>(a);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream) {
+    if (a.mfcc == nullptr || a.n_mfcc <= 0) return launch_db_nc<0>(a, stream);
+    switch (a.ncp) {
+        case 8: return launch_db_nc<8>(a, stream);
+        case 16: return launch_db_nc<16>(a, stream);
+        case 24: return launch_db_nc<24>(a, stream);
+        case 32: return launch_db_nc<32>(a, stream);
+        case 40: return launch_db_nc<40>(a, stream);
+        case 64: return launch_db_nc<64>(a, stream);
+        case 128: return launch_db_nc<128>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stand-alone librosa.power_to_db on (B, per_clip) arrays.
+// ---------------------------------------------------------------------------
+__global__ void rowmax_kernel(const float* __restrict__ in, unsigned int* clipmax, long long per_clip) {
+    const long long b = blockIdx.y;
+    const float* p = in + b * per_clip;
+    float m = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_clip;
+         i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(p[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(clipmax) + b, __float_as_int(m));
+}
+cudaError_t launch_rowmax(const float* in, unsigned int* clipmax, long long B, long long per_clip,
+                          cudaStream_t stream) {
+    if (B <= 0 || per_clip <= 0) return cudaSuccess;
+    int gx = (int)((per_clip + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    rowmax_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(in, clipmax, per_clip);
+    g_launches++;
+    return cudaGetLastError();
+}
+__global__ void power_to_db_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                   const unsigned int* __restrict__ clipmax, long long per_clip,
+                                   int ref_mode, float ref_value, float amin, float top_db) {
+    const long long b = blockIdx.y;
+    const float pmax = __uint_as_float(clipmax[b]);
+    const float maxa = db10(fmaxf(amin, pmax));
+    const float ref_db = (ref_mode == 1) ? maxa : db10(fmaxf(amin, fabsf(ref_value)));
+    const float floor_db = (top_db >= 0.0f) ? (maxa - ref_db) - top_db : -CUDART_INF_F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_clip;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float v = db10(fmaxf(amin, fabsf(in[b * per_clip + i]))) - ref_db;
+        out[b * per_clip + i] = fmaxf(v, floor_db);
+    }
+}
+cudaError_t launch_power_to_db(const float* in, float* out, const unsigned int* clipmax, long long B,
+                               long long per_clip, int ref_mode, float ref_value, float amin,
+                               float top_db, cudaStream_t stream) {
+    if (B <= 0 || per_clip <= 0) return cudaSuccess;
+    int gx = (int)((per_clip + 256 * 4 - 1) / (256 * 4));
+    if (gx < 1) gx = 1;
+    if (gx > 256) gx = 256;
+    power_to_db_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(in, out, clipmax, per_clip, ref_mode,
+                                                                  ref_value, amin, top_db);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Time pooling: np.mean / np.std (ddof=0) over frames, one warp per feature row
+// ([R] src/1_preprocessing.py:115-124, src/1_preprocessing_advanced.py:144-151).
+// ---------------------------------------------------------------------------
+__global__ void pool_kernel(const float* __restrict__ logmel, const float* __restrict__ mfcc,
+                            const float* __restrict__ stats, long long B, int n_mels, int n_mfcc,
+                            int T, float* __restrict__ pooled) {
+    const int rows = n_mels + n_mfcc + 5;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= B * rows) return;
+    const long long b = wid / rows;
+    const int r = (int)(wid - b * rows);
+    const float* src;
+    int o_mean, o_std;
+    if (r < n_mels) {
+        src = logmel + ((size_t)b * n_mels + r) * T;
+        o_mean = r; o_std = n_mels + r;
+    } else if (r < n_mels + n_mfcc) {
+        const int c = r - n_mels;
+        src = mfcc + ((size_t)b * n_mfcc + c) * T;
+        o_mean = 2 * n_mels + c; o_std = 2 * n_mels + n_mfcc + c;
+    } else {
+        const int s = r - n_mels - n_mfcc;
+        src = stats + ((size_t)b * 5 + s) * T;
+        o_mean = 2 * n_mels + 2 * n_mfcc + 2 * s; o_std = o_mean + 1;
+    }
+    float sum = 0.0f;
+    for (int i = lane; i < T; i += 32) sum += src[i];
+    sum = warp_sum(sum);
+    const float mean = sum / float(T);
+    float var = 0.0f;
+    for (int i = lane; i < T; i += 32) { const float d = src[i] - mean; var = fmaf(d, d, var); }
+    var = warp_sum(var);
+    if (lane == 0) {
+        float* out = pooled + (size_t)b * (2 * n_mels + 2 * n_mfcc + 10);
+        out[o_mean] = mean;
+        out[o_std] = sqrtf(var / float(T));
+    }
+}
+cudaError_t launch_pool(const float* logmel, const float* mfcc, const float* stats, long long B,
+                        int n_mels, int n_mfcc, int T, float* pooled, cudaStream_t stream) {
+    if (mfcc == nullptr) n_mfcc = 0;
+    const long long warps = B * (n_mels + n_mfcc + 5);
+    if (warps <= 0) return cudaSuccess;
+    pool_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(logmel, mfcc, stats, B, n_mels, n_mfcc,
+                                                                 T, pooled);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// [R] src/1_preprocessing_advanced.py:108-112: crop to `fixed` frames, or right-pad
+// with the clip's minimum.  One CTA per clip.
+// ---------------------------------------------------------------------------
+__global__ void fix_frames_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int T,
+                                  int fixed) {
+    __shared__ float s_min[32];
+    const long long b = blockIdx.x;
+    const float* src = in + (size_t)b * rows * T;
+    float* dst = out + (size_t)b * rows * fixed;
+    float fill = 0.0f;
+    if (T < fixed) {
+        float m = CUDART_INF_F;
+        for (int i = threadIdx.x; i < rows * T; i += blockDim.x) m = fminf(m, src[i]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, d));
+        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+        __syncthreads();
+        m = CUDART_INF_F;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fminf(m, s_min[i]);
+        fill = m;
+    }
+    const int keep = min(T, fixed);
+    for (int i = threadIdx.x; i < rows * fixed; i += blockDim.x) {
+        const int r = i / fixed, c = i - r * fixed;
+        dst[i] = (c < keep) ? src[(size_t)r * T + c] : fill;
+    }
+}
+cudaError_t launch_fix_frames(const float* in, float* out, long long B, int rows, int T, int fixed,
+                              cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    fix_frames_kernel<<<(unsigned)B, 256, 0, stream>>>(in, out, rows, T, fixed);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// FP32 roofline denominator: independent FMA chains, every SM sub-partition busy.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float seed) {
+    float x0 = seed + threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+    float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    const float a = 0.999f, c = 0.001f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, c); x1 = fmaf(x1, a, c); x2 = fmaf(x2, a, c); x3 = fmaf(x3, a, c);
+            x4 = fmaf(x4, a, c); x5 = fmaf(x5, a, c); x6 = fmaf(x6, a, c); x7 = fmaf(x7, a, c);
+        }
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456f) out[0] = r;
+}
+cudaError_t measure_fp32_peak(double* tflops) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, grid = sms * 8;
+    fma_peak_kernel<<<grid, 256>>>(d, 64, 1.0f);          // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<grid, 256>>>(d, iters, 1.0f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * 16.0 * double(iters) * 256.0 * double(grid);
+        const double tf = flops / (double(ms) * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    g_launches += 6;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return cudaGetLastError();
+}
+
+}  // namespace hlmc

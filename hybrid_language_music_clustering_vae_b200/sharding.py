@@ -1,0 +1,90 @@
+"""Multi-GPU sharding of a clip batch.
+
+Clips are independent, so there is no collective on the data path: rank r takes
+the contiguous block ``shard_bounds(B, r, world)``, runs it on its own GPU and
+streams, and the results meet in host memory (``gather_host`` across processes,
+or plain slice writes across threads in ``extract_multi_gpu``).
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+
+def shard_bounds(B: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of rank `rank`: ceil(B/world) clips each, last ranks may be short."""
+    per = -(-B // world) if world > 0 else B
+    lo = min(B, rank * per)
+    hi = min(B, lo + per)
+    return lo, hi
+
+
+def gather_host(local: np.ndarray, B: int, rank: int, world: int, group=None, dst: int = 0):
+    """Host gather of per-rank slices (leading axis) onto rank `dst`; returns None elsewhere.
+
+    Uses a gloo (CPU) group: the data path needs no NCCL collective.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    lo, hi = shard_bounds(B, rank, world)
+    assert local.shape[0] == hi - lo, (local.shape, lo, hi)
+    per = -(-B // world)
+    pad = np.zeros((per,) + local.shape[1:], dtype=local.dtype)
+    pad[: hi - lo] = local
+    t = torch.from_numpy(pad)
+    if rank == dst:
+        bufs = [torch.empty_like(t) for _ in range(world)]
+        dist.gather(t, gather_list=bufs, dst=dst, group=group)
+        out = np.empty((B,) + local.shape[1:], dtype=local.dtype)
+        for r in range(world):
+            l, h = shard_bounds(B, r, world)
+            out[l:h] = bufs[r].numpy()[: h - l]
+        return out
+    dist.gather(t, gather_list=None, dst=dst, group=group)
+    return None
+
+
+def extract_multi_gpu(waves: np.ndarray, devices, extractor_kwargs: dict, **extract_kw):
+    """Single-process variant: one host thread and one plan per device, outputs written
+    into slices of shared host arrays (the "host gather")."""
+    from .core import FeatureExtractor
+
+    B = waves.shape[0]
+    world = len(devices)
+    exs = [FeatureExtractor(device=d, **extractor_kwargs) for d in devices]
+    T = exs[0].num_frames(waves.shape[1])
+    want = dict(logmel=True, mfcc=True, stats=True, status=True, pooled=False)
+    want.update({k: v for k, v in extract_kw.items() if k in want})
+    out = {}
+    if want["logmel"]:
+        out["logmel"] = np.empty((B, exs[0].n_mels, T), np.float32)
+    if want["mfcc"] and exs[0].n_mfcc > 0:
+        out["mfcc"] = np.empty((B, exs[0].n_mfcc, T), np.float32)
+    if want["stats"]:
+        out["stats"] = np.empty((B, 5, T), np.float32)
+    if want["status"]:
+        out["status"] = np.empty((B,), np.int32)
+    if want["pooled"]:
+        out["pooled"] = np.empty((B, exs[0].pooled_width(exs[0].n_mfcc > 0)), np.float32)
+    errs = []
+
+    def work(r):
+        try:
+            lo, hi = shard_bounds(B, r, world)
+            if hi > lo:
+                exs[r].extract_host(waves[lo:hi], out={k: v[lo:hi] for k, v in out.items()}, **extract_kw)
+        except Exception as e:  # surfaced after join
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for ex in exs:
+        ex.close()
+    if errs:
+        raise errs[0]
+    return out

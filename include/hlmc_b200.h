@@ -1,0 +1,190 @@
+/*
+ * hlmc_b200.h -- C ABI of the B200-native audio feature extractor.
+ *
+ * Drop-in boundary for the feature-extraction hot path of
+ * Shahriar1638/Hybrid-Language-Music-Clustering-VAE.  The reference has no FFI
+ * of its own for this path: its boundary is the Python call surface of librosa
+ * used in src/1_preprocessing.py and src/1_preprocessing_advanced.py.  Every
+ * entry point below names the librosa call (and the reference call site) whose
+ * arithmetic it replaces; the ctypes binding a maintainer adds on the
+ * reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; no torch / numpy types cross this boundary
+ *   - all buffers are caller-owned; the library never returns owning pointers
+ *   - "d_" = device pointer on the plan's device, "h_" = host pointer
+ *     (pinned for full speed; pageable works, slower)
+ *   - every function returns 0 on success or a negative hlmc_status; the text
+ *     of the last error on the calling thread is hlmc_last_error()
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream)
+ *   - layouts are librosa's: feature arrays are (clip, feature, frame),
+ *     frame fastest (C order)
+ */
+#ifndef HLMC_B200_H
+#define HLMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HLMC_ABI_VERSION 1
+
+typedef enum hlmc_status {
+    HLMC_OK = 0,
+    HLMC_ERR_PARAM = -1,      /* librosa would raise ParameterError           */
+    HLMC_ERR_UNSUPPORTED = -2,/* valid for librosa, not implemented here      */
+    HLMC_ERR_CUDA = -3,       /* CUDA runtime error (see hlmc_last_error)     */
+    HLMC_ERR_NOMEM = -4
+} hlmc_status;
+
+/* pad_mode of librosa.stft / feature.rms (np.pad modes that librosa accepts) */
+enum { HLMC_PAD_CONSTANT = 0, HLMC_PAD_REFLECT = 1, HLMC_PAD_EDGE = 2 };
+/* `ref` of librosa.power_to_db: a number, or np.max evaluated per clip       */
+enum { HLMC_REF_VALUE = 0, HLMC_REF_MAX = 1 };
+/* `norm` of librosa.filters.mel */
+enum { HLMC_MELNORM_NONE = 0, HLMC_MELNORM_SLANEY = 1 };
+/* rows of the `stats` output, in the order the reference stores them
+ * ([R] src/1_preprocessing.py:85-91 dict order; _advanced.py:149)            */
+enum { HLMC_STAT_CENTROID = 0, HLMC_STAT_BANDWIDTH = 1, HLMC_STAT_ROLLOFF = 2,
+       HLMC_STAT_ZCR = 3, HLMC_STAT_RMS = 4, HLMC_NUM_STATS = 5 };
+/* per-clip status bits (the batched analogue of the scripts' per-file
+ * try/except: [R] src/1_preprocessing.py:238-251, _advanced.py:165-183)      */
+enum { HLMC_CLIP_NONFINITE = 1 };
+
+/* One POD block holding every keyword the reference passes (or leaves at its
+ * librosa default) at the call sites of SURVEY.md section 8(a).              */
+typedef struct hlmc_params {
+    int32_t sr;            /* sr=22050                                        */
+    int32_t n_fft;         /* n_fft=2048 (power of two, 64..8192)             */
+    int32_t hop_length;    /* hop_length=512                                  */
+    int32_t win_length;    /* win_length=None -> n_fft                        */
+    int32_t center;        /* center=True                                     */
+    int32_t pad_mode;      /* HLMC_PAD_*; librosa>=0.10 default "constant"    */
+    int32_t n_mels;        /* n_mels=128                                      */
+    float   fmin;          /* fmin=0.0                                        */
+    float   fmax;          /* fmax=None -> sr/2 (pass <=0 for None)           */
+    int32_t htk;           /* htk=False                                       */
+    int32_t mel_norm;      /* HLMC_MELNORM_*; default slaney                  */
+    float   power;         /* melspectrogram power=2.0 (1.0 or 2.0)           */
+    int32_t n_mfcc;        /* n_mfcc=20 (scripts: 40); 0 = no MFCC            */
+    float   lifter;        /* lifter=0                                        */
+    int32_t ref_mode;      /* HLMC_REF_*; scripts use ref=np.max              */
+    float   ref_value;     /* ref when ref_mode == HLMC_REF_VALUE             */
+    float   amin;          /* amin=1e-10                                      */
+    float   top_db;        /* top_db=80.0; negative = None                    */
+    float   roll_percent;  /* spectral_rolloff roll_percent=0.85              */
+    float   zcr_threshold; /* zero_crossings threshold=1e-10                  */
+} hlmc_params;
+
+typedef struct hlmc_plan hlmc_plan;   /* opaque; one per (params, device)     */
+
+/* ABI / diagnostics ------------------------------------------------------- */
+int         hlmc_abi_version(void);
+const char *hlmc_last_error(void);
+/* Fill *p with the librosa defaults listed above.                            */
+void        hlmc_params_default(hlmc_params *p);
+/* T of librosa.util.frame after centre padding: 1 + n // hop (center) or
+ * 1 + (n - n_fft) // hop.  Returns <0 (HLMC_ERR_PARAM) when librosa raises.  */
+int64_t     hlmc_num_frames(const hlmc_params *p, int64_t n);
+/* Number of this library's kernels launched by the calling process so far.   */
+int64_t     hlmc_launch_count(void);
+
+/* Plan ---------------------------------------------------------------------
+ * Builds on the host, in float64 rounded once to float32, and uploads: the
+ * analysis window (librosa.filters.get_window + util.pad_center), FFT
+ * twiddles, the banded mel filterbank (librosa.filters.mel) and the DCT-II
+ * matrix (scipy.fftpack.dct type 2, norm="ortho", first n_mfcc rows).
+ *   window    : NULL -> periodic Hann of win_length; else win_length floats
+ *               (what scipy.signal.get_window(window, win_length) returned)
+ *   mel_basis : NULL -> built from params; else dense (n_mels, 1+n_fft/2)    */
+int  hlmc_plan_create(const hlmc_params *params, const double *window,
+                      const float *mel_basis, int device, hlmc_plan **out);
+void hlmc_plan_destroy(hlmc_plan *plan);
+/* Kernel selection.  n_fft == 2048 (the only size the reference uses) runs the
+ * register-FFT kernel; other power-of-two sizes run the shared-memory FFT
+ * kernel.  generic != 0 forces the latter (tests cross-check the two); the
+ * environment variable HLMC_FORCE_GENERIC=1 does the same at plan creation.  */
+int  hlmc_plan_set_path(hlmc_plan *plan, int generic);
+int  hlmc_plan_uses_fast_path(const hlmc_plan *plan);
+/* Copy of the filterbank / DCT the plan uses (for inspection and tests).     */
+int  hlmc_plan_mel_basis(const hlmc_plan *plan, float *h_out /* n_mels*(1+n_fft/2) */);
+int  hlmc_plan_dct_basis(const hlmc_plan *plan, float *h_out /* n_mfcc*n_mels */);
+
+/* Fused extraction, device-resident ---------------------------------------
+ * One call replaces, for a batch of B clips, the librosa chain
+ *   feature.melspectrogram -> power_to_db          ([R] 1_preprocessing.py:50-57,
+ *                                                       _advanced.py:99-106,125-129)
+ *   feature.mfcc                                   ([R] 1_preprocessing.py:63-69)
+ *   feature.spectral_centroid / spectral_bandwidth / spectral_rolloff /
+ *   zero_crossing_rate / rms                       ([R] 1_preprocessing.py:75-83,
+ *                                                       _advanced.py:133-137)
+ * computed from ONE STFT per frame instead of the reference's five.
+ *   d_wave   : (B, n) float32 waveforms, row pitch `pitch` elements (>= n)
+ *   d_logmel : (B, n_mels, T) float32   power_to_db(melspectrogram) [required]
+ *   d_mfcc   : (B, n_mfcc, T) float32   or NULL
+ *   d_stats  : (B, 5, T) float32        rows HLMC_STAT_*, or NULL
+ *   d_status : (B) int32                HLMC_CLIP_* bits, or NULL
+ *   d_clipmax: (B) float32 workspace    per-clip max of the mel power
+ * power_to_db's ref=np.max and top_db are evaluated PER CLIP (the scripts call
+ * librosa once per clip), not over the whole batch.  MFCC follows librosa:
+ * DCT of power_to_db(mel, ref=1.0, amin=1e-10, top_db=80).                   */
+int hlmc_extract_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t n,
+                        int64_t pitch, float *d_logmel, float *d_mfcc, float *d_stats,
+                        int32_t *d_status, float *d_clipmax, void *stream);
+
+/* Same, but the mel output is |X|^power projected on the filterbank WITHOUT
+ * the dB step (librosa.feature.melspectrogram alone).                        */
+int hlmc_melspectrogram_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t n,
+                               int64_t pitch, float *d_mel, float *d_stats,
+                               int32_t *d_status, void *stream);
+
+/* librosa.stft: (B, 1+n_fft/2, T) complex64 (interleaved re,im).             */
+int hlmc_stft_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t n,
+                     int64_t pitch, float *d_spec, void *stream);
+
+/* librosa.power_to_db on an arbitrary (B, rows, T) float32 array, ref / top_db
+ * per leading index.  In place when d_out == d_in.                           */
+int hlmc_power_to_db_device(const float *d_in, float *d_out, int64_t B, int64_t rows,
+                            int64_t T, int32_t ref_mode, float ref_value, float amin,
+                            float top_db, float *d_clipmax, int device, void *stream);
+
+/* Time pooling of the scripts ([R] 1_preprocessing.py:115-124,
+ * _advanced.py:144-151): np.mean / np.std(ddof=0) over frames of every logmel
+ * row, every MFCC row and the five statistics.
+ *   d_pooled : (B, 2*n_mels + 2*n_mfcc + 10) float32 =
+ *              [mel mean | mel std | mfcc mean | mfcc std | (mean,std) x 5]
+ *   d_mfcc may be NULL (then the MFCC columns are omitted: 2*n_mels + 10).   */
+int hlmc_pool_device(hlmc_plan *plan, const float *d_logmel, const float *d_mfcc,
+                     const float *d_stats, int64_t B, int64_t T, float *d_pooled,
+                     void *stream);
+
+/* [R] _advanced.py:108-112: crop to fixed_time_steps frames, or right-pad
+ * with the clip's minimum.  d_out: (B, rows, fixed) float32.                 */
+int hlmc_fix_frames_device(const float *d_in, float *d_out, int64_t B, int64_t rows,
+                           int64_t T, int64_t fixed, int device, void *stream);
+
+/* Fused extraction, host buffers -------------------------------------------
+ * The reference-facing call: waveforms in host memory in, features in host
+ * memory out.  Internally chunks the batch, and overlaps H2D copies, kernels
+ * and D2H copies on `n_streams` streams.  Blocking.  Any output may be NULL.
+ *   chunk_clips <= 0 -> chosen by the library.                               */
+int hlmc_extract_host(hlmc_plan *plan, const float *h_wave, int64_t B, int64_t n,
+                      int64_t h_pitch, float *h_logmel, float *h_mfcc, float *h_stats,
+                      int32_t *h_status, float *h_pooled, int64_t chunk_clips, int n_streams);
+
+/* Bytes moved by the last hlmc_extract_host call on this plan.               */
+void hlmc_last_transfer_bytes(const hlmc_plan *plan, int64_t *h2d, int64_t *d2h);
+
+/* Measurement helper: a dependent-FMA micro-benchmark that returns the
+ * achieved FP32 TFLOP/s of the plan's device (the FP32-pipe roofline
+ * denominator of SURVEY.md 8(d)); no product path calls it.                  */
+int hlmc_measure_fp32_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLMC_B200_H */

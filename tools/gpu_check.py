@@ -1,0 +1,52 @@
+"""Diagnostic (not a test): prints parity metrics of the CUDA path against the oracle."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+import __graft_entry__ as g
+g.build()
+import hybrid_language_music_clustering_vae_b200 as hl
+from parity import oracle_clip, compare_clip
+
+def run(B, n, generic=False, **kw):
+    y = hl.synth.synth_batch(B, n, seed=11)
+    okw = dict(kw)
+    ex = hl.FeatureExtractor(n_mfcc=40, ref=np.max, **kw)
+    if generic: ex.force_generic(True)
+    out = ex.extract_device(torch.from_numpy(y).cuda())
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    worst = {}
+    for i in range(B):
+        want = oracle_clip(y[i], n_mfcc=40, **okw)
+        got = {k: out[k][i] for k in ("logmel", "mfcc", "stats")}
+        m = compare_clip(got, want, n_fft=kw.get("n_fft", 2048), sr=22050)
+        for k, v in m.items():
+            if isinstance(v, bool): worst[k] = worst.get(k, True) and v
+            else: worst[k] = max(worst.get(k, 0), v)
+    print(f"B={B} n={n} generic={generic} fast={ex.uses_fast_path()} {kw}:")
+    print("   ", {k: (f"{v:.3g}" if isinstance(v, float) else v) for k, v in worst.items()}, "status", out["status"].tolist()[:8], flush=True)
+
+print(torch.cuda.get_device_name(0))
+for gen in (True, False):
+    run(20, 22050, generic=gen)
+    run(6, 66150, generic=gen, pad_mode="reflect")
+    run(4, 2047, generic=gen)
+    run(3, 511, generic=gen, pad_mode="reflect")
+run(4, 30000, n_fft=1024, hop_length=256)
+run(4, 30000, n_fft=512, hop_length=128)
+run(4, 30000, n_fft=4096, hop_length=1024)
+run(2, 661500)
+# throughput quick look
+ex = hl.FeatureExtractor(n_mfcc=40, ref=np.max)
+y = torch.randn(2000, 66152, device="cuda")[:, :66150] * 0.1
+for _ in range(2):
+    out = ex.extract_device(y)
+torch.cuda.synchronize()
+t0 = time.time()
+for _ in range(3):
+    out = ex.extract_device(y, out=out)
+torch.cuda.synchronize()
+dt = (time.time() - t0) / 3
+print(f"2000 clips x 3 s: {dt*1e3:.2f} ms -> {2000/dt:.0f} clips/s")
+print("fp32 peak TFLOP/s", hl.measure_fp32_peak(0))
