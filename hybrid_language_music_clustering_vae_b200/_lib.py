@@ -19,6 +19,7 @@ EXPORTS = (
     "hlmc_extract_device", "hlmc_melspectrogram_device", "hlmc_stft_device",
     "hlmc_power_to_db_device", "hlmc_pool_device", "hlmc_fix_frames_device",
     "hlmc_extract_host", "hlmc_last_transfer_bytes", "hlmc_measure_fp32_peak",
+    "hlmc_plan_set_timing", "hlmc_plan_read_timing",
 )
 
 HLMC_OK, HLMC_ERR_PARAM, HLMC_ERR_UNSUPPORTED, HLMC_ERR_CUDA, HLMC_ERR_NOMEM = 0, -1, -2, -3, -4
@@ -73,6 +74,8 @@ def _load():
     lib.hlmc_last_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.hlmc_last_transfer_bytes.restype = None
     lib.hlmc_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.hlmc_plan_set_timing.argtypes = [vp, C.c_int]
+    lib.hlmc_plan_read_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("hlmc_abi_version",):

@@ -149,6 +149,15 @@ class FeatureExtractor:
     def force_generic(self, flag: bool = True):
         _check(lib.hlmc_plan_set_path(self._plan, int(bool(flag))))
 
+    def set_timing(self, enable: bool):
+        _check(lib.hlmc_plan_set_timing(self._plan, int(bool(enable))))
+
+    def read_timing(self):
+        """-> (frames-kernel ms, dB+DCT-kernel ms, calls) since the last read."""
+        f, d, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        _check(lib.hlmc_plan_read_timing(self._plan, C.byref(f), C.byref(d), C.byref(n)))
+        return float(f.value), float(d.value), int(n.value)
+
     def mel_basis(self) -> np.ndarray:
         out = np.empty((self.n_mels, self.n_bins), dtype=np.float32)
         _check(lib.hlmc_plan_mel_basis(self._plan, out.ctypes.data_as(C.c_void_p)))

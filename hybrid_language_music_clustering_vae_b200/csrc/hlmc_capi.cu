@@ -51,6 +51,9 @@ struct hlmc_plan {
     std::vector<HostPipeSlot> slots;
     int64_t slot_chunk = 0, slot_n = 0; int slot_flags = 0;
     int64_t last_h2d = 0, last_d2h = 0;
+    // optional per-kernel timing (events recorded on the launching stream)
+    int timing = 0;
+    std::vector<cudaEvent_t> ev;      // triples: before frames, after frames, after db_dct
 };
 
 // ---------------------------------------------------------------------------
@@ -375,14 +378,50 @@ int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t
     if (d_mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
     CK(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaEvent_t ev3[3] = {nullptr, nullptr, nullptr};
+    if (plan->timing) {
+        for (auto& e : ev3) CK(cudaEventCreate(&e));
+        CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));   // keep the memsets out of the bracket
+    }
+    if (plan->timing) CK(cudaEventRecord(ev3[0], st));
     rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_logmel, d_stats, d_status, d_clipmax, nullptr, st);
     if (rc != HLMC_OK) return rc;
+    if (plan->timing) CK(cudaEventRecord(ev3[1], st));
     DbArgs d{};
     d.mel = d_logmel; d.mfcc = d_mfcc; d.clipmax = reinterpret_cast<const unsigned int*>(d_clipmax);
     d.dct_t = plan->d_dct_t; d.B = (int)B; d.n_mels = plan->p.n_mels; d.n_mfcc = plan->p.n_mfcc;
     d.ncp = plan->ncp; d.T = (int)T; d.ref_mode = plan->p.ref_mode; d.ref_value = plan->p.ref_value;
     d.amin = plan->p.amin; d.top_db = plan->p.top_db;
     CK(launch_db_dct(d, st));
+    if (plan->timing) {
+        CK(cudaEventRecord(ev3[2], st));
+        for (auto& e : ev3) plan->ev.push_back(e);
+    }
+    return HLMC_OK;
+}
+
+int hlmc_plan_set_timing(hlmc_plan* plan, int enable) {
+    if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
+    plan->timing = enable ? 1 : 0;
+    return HLMC_OK;
+}
+
+int hlmc_plan_read_timing(hlmc_plan* plan, double* frames_ms, double* db_ms, int64_t* calls) {
+    if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
+    double f = 0.0, d = 0.0;
+    int64_t n = 0;
+    for (size_t i = 0; i + 2 < plan->ev.size(); i += 3) {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventSynchronize(plan->ev[i + 2]));
+        CK(cudaEventElapsedTime(&a, plan->ev[i], plan->ev[i + 1]));
+        CK(cudaEventElapsedTime(&b, plan->ev[i + 1], plan->ev[i + 2]));
+        f += a; d += b; ++n;
+    }
+    for (auto e : plan->ev) cudaEventDestroy(e);
+    plan->ev.clear();
+    if (frames_ms) *frames_ms = f;
+    if (db_ms) *db_ms = d;
+    if (calls) *calls = n;
     return HLMC_OK;
 }
 

@@ -136,6 +136,13 @@ int hlmc_extract_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t
                         int64_t pitch, float *d_logmel, float *d_mfcc, float *d_stats,
                         int32_t *d_status, float *d_clipmax, void *stream);
 
+/* Per-kernel timing of hlmc_extract_device for the roofline report: when
+ * enabled, CUDA events are recorded on the launching stream around the frames
+ * kernel and around the dB+DCT kernel.  hlmc_plan_read_timing synchronises on
+ * them, returns the summed durations (ms) and the number of calls, and resets. */
+int hlmc_plan_set_timing(hlmc_plan *plan, int enable);
+int hlmc_plan_read_timing(hlmc_plan *plan, double *frames_ms, double *db_ms, int64_t *calls);
+
 /* Same, but the mel output is |X|^power projected on the filterbank WITHOUT
  * the dB step (librosa.feature.melspectrogram alone).                        */
 int hlmc_melspectrogram_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t n,
