@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -250,33 +252,80 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         FastTables ft{};
         const int ng = (nm + 31) / 32;
         ft.n_groups = ng;
+        // meta: [0..7] float4 steps per group, [8..15] weight offset per group, then the
+        // (shifted) first tap of every (group, lane) in the padded layout q(k) = k + k/16
         std::vector<int> meta(2 * kMaxMelGroups + 32 * ng, 0);
         std::vector<float> melw;
-        int max_gmax = 0;
         auto qof = [](int k) { return k + (k >> 4); };
+        const int kReadEnd = 1105;           // the kernel keeps scratch [0, 1105) finite
         for (int g = 0; g < ng; ++g) {
+            int ql[32], qlen[32];
             int gmax = 0;
             for (int l = 0; l < 32; ++l) {
                 const int m = 32 * g + l;
                 if (m < nm && len[m] > 0) {
-                    const int ql = qof(lo[m]), qh = qof(lo[m] + len[m] - 1);
-                    if (qh - ql + 1 > gmax) gmax = qh - ql + 1;
+                    ql[l] = qof(lo[m]);
+                    qlen[l] = qof(lo[m] + len[m] - 1) - ql[l] + 1;
+                } else { ql[l] = 0; qlen[l] = 0; }
+                if (qlen[l] > gmax) gmax = qlen[l];
+            }
+            // Shift each lane's first tap down (zero weights in front) so that the 32 lanes
+            // start on 32 different banks: the gather is then conflict-free at every step.
+            // Bipartite matching lanes -> banks; grow the common length G until one exists.
+            int G = (gmax + 3) & ~3, shiftv[32];
+            for (int l = 0; l < 32; ++l) shiftv[l] = 0;
+            bool ok = (G == 0);
+            for (int tries = 0; !ok && tries < 12; ++tries, G += 4) {
+                std::vector<std::vector<int>> opt(32);   // candidate shifts per lane
+                bool feasible = true;
+                for (int l = 0; l < 32; ++l) {
+                    if (qlen[l] == 0) { for (int s = 0; s < 32; ++s) opt[l].push_back(-s); continue; }  // start = s
+                    const int smin = std::max(0, ql[l] + G - kReadEnd);
+                    const int smax = std::min(G - qlen[l], ql[l]);
+                    if (smin > smax) { feasible = false; break; }
+                    for (int s = smin; s <= smax && s < smin + 32; ++s) opt[l].push_back(s);
+                }
+                if (!feasible) continue;
+                int owner[32]; for (int& o : owner) o = -1;
+                auto bank_of = [&](int l, int s) { return ((qlen[l] == 0 ? -s : ql[l] - s) % 32 + 32) % 32; };
+                std::vector<char> seen(32);
+                std::function<bool(int)> aug = [&](int l) -> bool {
+                    for (int s : opt[l]) {
+                        const int bk = bank_of(l, s);
+                        if (seen[bk]) continue;
+                        seen[bk] = 1;
+                        if (owner[bk] < 0 || aug(owner[bk])) { owner[bk] = l; return true; }
+                    }
+                    return false;
+                };
+                int matched = 0;
+                for (int l = 0; l < 32; ++l) { std::fill(seen.begin(), seen.end(), 0); if (aug(l)) ++matched; }
+                if (matched == 32) {
+                    for (int bk = 0; bk < 32; ++bk) {
+                        const int l = owner[bk];
+                        for (int s : opt[l]) if (bank_of(l, s) == bk) { shiftv[l] = s; break; }
+                    }
+                    ok = true;
+                    break;
                 }
             }
-            meta[g] = gmax;
+            if (!ok) {   // no conflict-free placement: keep the natural starts (still correct)
+                G = (gmax + 3) & ~3;
+                for (int l = 0; l < 32; ++l) shiftv[l] = std::max(0, ql[l] + G - kReadEnd);
+            }
+            meta[g] = G / 4;
             meta[kMaxMelGroups + g] = (int)melw.size();
-            if (gmax > max_gmax) max_gmax = gmax;
             const size_t base = melw.size();
-            melw.resize(base + (size_t)32 * gmax, 0.0f);
+            melw.resize(base + (size_t)32 * G, 0.0f);
             for (int l = 0; l < 32; ++l) {
                 const int m = 32 * g + l;
-                if (m >= nm || len[m] == 0) { meta[2 * kMaxMelGroups + m] = 0; continue; }
-                const int ql = qof(lo[m]), qh = qof(lo[m] + len[m] - 1);
-                meta[2 * kMaxMelGroups + m] = ql;
-                for (int q = ql; q <= qh; ++q) {
+                const int start = (qlen[l] == 0) ? -shiftv[l] : ql[l] - shiftv[l];
+                meta[2 * kMaxMelGroups + 32 * g + l] = start;
+                if (qlen[l] == 0) continue;
+                for (int q = ql[l]; q < ql[l] + qlen[l]; ++q) {
                     if (q % 17 == 16) continue;                     // pad slot
-                    const int k = q - q / 17;
-                    melw[base + (size_t)32 * (q - ql) + l] = pl->mel_dense[(size_t)m * F + k];
+                    const int k = q - q / 17, i = q - start;
+                    melw[base + ((size_t)(i / 4) * 32 + l) * 4 + (i % 4)] = pl->mel_dense[(size_t)m * F + k];
                 }
             }
         }
@@ -287,7 +336,7 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         ft.mel_meta = ft.tw2 + 16 * 32 * 2;
         ft.mel_w = r4(ft.mel_meta + (int)meta.size());
         ft.total = r4(ft.mel_w + (int)melw.size());
-        ft.scr = r4(1089 + max_gmax + 1);
+        ft.scr = r4(kReadEnd + 3);
         std::vector<float> blob(ft.total, 0.0f);
         memcpy(&blob[ft.win], win.data(), N * 4);
         for (int k1 = 1; k1 < 32; ++k1)

@@ -108,44 +108,41 @@ __device__ __forceinline__ float sample_edge(const float* __restrict__ clip, int
 }
 
 // ---------------------------------------------------------------------------
-// Fast path: n_fft = 2048, one warp per frame, FFT in registers.
+// Fast path: n_fft = 2048.  Persistent CTAs of NW fully independent warps; each
+// warp walks a contiguous run of (clip, frame) pairs and owns one shared-memory
+// buffer that is first the TMA landing zone for the frame's 2048 samples and
+// then the scratch for the FFT transposes and the mel gather.  There is no
+// CTA-wide barrier after setup.
 // ---------------------------------------------------------------------------
-constexpr int kHdrFloats = 8;        // 2 mbarriers (16 B) + tile max [2] + pad
+constexpr int kWarpBufFloats = 2 * 32 * 33 + 8;   // 32x33 float2 transpose tile (+ slack) = 2120
 
 __host__ __device__ constexpr int pos32(int k) { return fftreg::fft_pos<32>(k); }
 
 struct FastSmemLayout {
-    int tables, seg, seg_cap, stage, stage_sz, sstage, sstage_sz, scratch, total;
+    int bars, tables, wbuf, wb, total;   // float offsets; wb = floats per warp buffer
 };
-__host__ __device__ inline FastSmemLayout fast_layout(const FastTables& ft, int nw, int hop,
-                                                       int n_mels) {
+__host__ __device__ inline FastSmemLayout fast_layout(const FastTables& ft, int nw) {
     FastSmemLayout L;
-    L.tables = kHdrFloats;
-    L.seg = L.tables + ft.total;
-    L.seg_cap = ((nw - 1) * hop + kFastNfft + 4 + 3) & ~3;
-    L.stage = L.seg + 2 * L.seg_cap;
-    L.stage_sz = (n_mels * (nw + 1) + 3) & ~3;
-    L.sstage = L.stage + 2 * L.stage_sz;
-    L.sstage_sz = (5 * nw + 3) & ~3;
-    L.scratch = L.sstage + 2 * L.sstage_sz;
-    L.total = L.scratch + nw * ft.scr;
+    L.bars = 0;                                   // nw mbarriers, 8 B each
+    L.tables = (2 * nw + 3) & ~3;
+    L.wbuf = L.tables + ft.total;
+    L.wb = (((ft.scr > kWarpBufFloats) ? ft.scr : kWarpBufFloats) + 3) & ~3;
+    L.total = L.wbuf + nw * L.wb;
     return L;
 }
 int fast_smem_bytes(const FastTables& ft, int nwarps, int n_fft, int hop, int n_mels) {
-    (void)n_fft;
-    return fast_layout(ft, nwarps, hop, n_mels).total * 4;
+    (void)n_fft; (void)hop; (void)n_mels;
+    return fast_layout(ft, nwarps).total * 4;
 }
-// Warps per CTA (= frames per tile): a multiple of 4 (one per SM sub-partition)
-// that wastes the fewest warp slots in the last tile of a clip.
-int pick_fast_warps(int T) {
-    int best = 16; double best_eff = -1.0;
-    const int cand[3] = {16, 12, 8};
-    for (int c : cand) {
-        int tiles = (T + c - 1) / c;
-        double eff = double(T) / double(tiles * c);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
-    }
-    return best;
+int pick_fast_warps(int T) { (void)T; return 16; }
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 template <int NW>
@@ -154,350 +151,314 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const FastSmemLayout L = fast_layout(ft, NW, a.hop, a.n_mels);
+    const FastSmemLayout L = fast_layout(ft, NW);
 
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
-    int* tilemax = reinterpret_cast<int*>(smem + 4);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
     float* tab = smem + L.tables;
     const float2* s_win = reinterpret_cast<const float2*>(tab + ft.win);
     const float2* s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + ft.tw2);
     const int* s_meta = reinterpret_cast<const int*>(tab + ft.mel_meta);
     const float* s_melw = tab + ft.mel_w;
-    float* sc = smem + L.scratch + warp * ft.scr;
+    float* sc = smem + L.wbuf + warp * L.wb;          // this warp's buffer
+    float2* sc2 = reinterpret_cast<float2*>(sc);
 
-    // ---- one-time CTA setup: tables -> smem, zero scratch/staging, barriers
+    // ---- one-time CTA setup: tables -> smem, zero the warp buffers, one mbarrier per warp
     for (int i = tid; i < ft.total / 4; i += NT)
         reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
-    for (int i = L.stage + tid; i < L.total; i += NT) smem[i] = 0.0f;
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        tilemax[0] = 0;
-        tilemax[1] = 0;
+    for (int i = L.wbuf + tid; i < L.total; i += NT) smem[i] = 0.0f;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    const int tiles_per_clip = (a.T + NW - 1) / NW;
-    const long long items = (long long)a.B * tiles_per_clip;
+    // ---- this warp's contiguous run of frames
+    const long long total = (long long)a.B * a.T;
+    const long long nwarps = (long long)gridDim.x * NW;
+    const long long per = (total + nwarps - 1) / nwarps;
+    const long long g0 = ((long long)blockIdx.x * NW + warp) * per;
+    const long long g1 = (g0 + per < total) ? g0 + per : total;
+    if (g0 >= g1) return;
+    int b = (int)(g0 / a.T);
+    int t = (int)(g0 - (long long)b * a.T);
+    uint32_t parity = 0;
+    float clip_max = 0.0f;
+    const float zthr = a.zcr_thr;
 
-    // Producer: one thread stages the samples a tile of NW frames touches.
-    auto issue_tile = [&](long long item, int buf) {
-        const int b = (int)(item / tiles_per_clip);
-        const int t0 = (int)(item - (long long)b * tiles_per_clip) * NW;
-        const int nf = min(NW, a.T - t0);
-        const int s_lo = max(0, t0 * a.hop - a.pad);
-        const int s_hi = min(a.n, (t0 + nf - 1) * a.hop - a.pad + kFastNfft);
-        const int cnt = s_hi - s_lo;
-        float* dst = smem + L.seg + buf * L.seg_cap;
-        if (cnt <= 0) { mbar_arrive(&mbar[buf]); return; }
-        const float* src = a.wave + (long long)b * a.pitch + s_lo;
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
-        const uintptr_t a0 = addr & ~uintptr_t(15);
-        const int shift = (int)((addr - a0) >> 2);
-        const int total = shift + cnt;
-        const int bulk = total & ~3;
-        const float* src0 = reinterpret_cast<const float*>(a0);
-        for (int i = bulk; i < total; ++i) dst[i] = __ldg(src0 + i);   // <= 3 tail floats
-        if (bulk > 0) {
-            mbar_arrive_expect_tx(&mbar[buf], (uint32_t)bulk * 4u);
-            tma_bulk_g2s(dst, src0, (uint32_t)bulk * 4u, &mbar[buf]);
-        } else {
-            mbar_arrive(&mbar[buf]);
-        }
-    };
+    // per-lane constants of the XOR-swizzled regroup (float2 units)
+    const int hb = lane >> 4;
+    const int lh = lane ^ hb;
+    const int base_lo = (lane << 4) ^ lane;
+    const int base_hi0 = ((16 * (64 - lane)) & 1023) ^ ((64 - lane) & 31);
+    const int base_hi = ((63 - lane) << 4) ^ (31 - lane);
 
-    long long it = blockIdx.x;
-    if (tid == 0 && it < items) issue_tile(it, 0);
-
-    const float nthr = -a.zcr_thr;
-
-    for (int k = 0; it < items; it += gridDim.x, ++k) {
-        const int buf = k & 1;
-        if (tid == 0 && it + gridDim.x < items) issue_tile(it + gridDim.x, buf ^ 1);
-
-        const int b = (int)(it / tiles_per_clip);
-        const int t0 = (int)(it - (long long)b * tiles_per_clip) * NW;
-        const int nf = min(NW, a.T - t0);
-        const int s_lo = max(0, t0 * a.hop - a.pad);
+    for (long long g = g0; g < g1; ++g) {
         const float* clip = a.wave + (long long)b * a.pitch;
-        const int shift = (int)((reinterpret_cast<uintptr_t>(clip + s_lo) & 15) >> 2);
-        const float* seg = smem + L.seg + buf * L.seg_cap;
-        float* stage = smem + L.stage + buf * L.stage_sz;
-        float* sstage = smem + L.sstage + buf * L.sstage_sz;
+        const int fs = t * a.hop - a.pad;              // first sample of the frame (clip coords)
+        const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
+        const int shift = (int)((addr & 15) >> 2);
+        int zc_edge = -1;
+        int off;
 
-        mbar_wait(&mbar[buf], (uint32_t)((k >> 1) & 1));
+        // ---- stage the frame's samples in this warp's buffer
+        if (interior && !(shift & 1)) {
+            if (lane == 0) {
+                const float* src0 = reinterpret_cast<const float*>(addr & ~uintptr_t(15));
+                const int tot = shift + kFastNfft;
+                const int bulk = tot & ~3;
+                for (int i = bulk; i < tot; ++i) sc[i] = __ldg(src0 + i);     // <= 3 tail floats
+                fence_proxy_async_smem();       // order earlier generic accesses before the async write
+                mbar_arrive_expect_tx(mbar, (uint32_t)bulk * 4u);
+                tma_bulk_g2s(sc, src0, (uint32_t)bulk * 4u, mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            off = shift;
+        } else {
+            // edge frame (or odd alignment): build the padded frame by hand; ZCR pads with "edge"
+            int zc = 0;
+            unsigned prev_last = 0u;
+            for (int c = 0; c < kFastNfft / 32; ++c) {
+                const int s = fs + 32 * c + lane;
+                sc[32 * c + lane] = sample_padded(clip, a.n, s, a.pad_mode);
+                const unsigned msk = __ballot_sync(FULL, sample_edge(clip, a.n, s) < -zthr);
+                zc += __popc((msk ^ (msk >> 1)) & 0x7fffffffu);
+                if (c > 0) zc += ((msk & 1u) != prev_last) ? 1 : 0;
+                prev_last = msk >> 31;
+            }
+            zc_edge = zc;
+            off = 0;
+            __syncwarp();
+        }
 
-        if (warp < nf) {
-            const int t = t0 + warp;
-            const int fs = t * a.hop - a.pad;          // first sample of the frame (clip coords)
-            const int off = fs - s_lo + shift;
-            const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
+        float vr[64], vi[64];
+        float ss = 0.0f;
+        unsigned za = 0u, zb = 0u;
 
-            float vr[64], vi[64];
-            float ss = 0.0f;
-            unsigned za = 0u, zb = 0u;
-
-            // ---- phase 0: frame -> registers; window; RMS and ZCR partials
-            if (interior && !(off & 1)) {
-                const float2* xp = reinterpret_cast<const float2*>(seg + off);
+        // ---- phase 0: frame -> registers; window; RMS and ZCR partials
+        {
+            const float2* xp = reinterpret_cast<const float2*>(sc + off);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 x = xp[lane + 32 * j];
-                    const float2 w = s_win[lane + 32 * j];
-                    ss = fmaf(x.x, x.x, ss);
-                    ss = fmaf(x.y, x.y, ss);
-                    za |= (x.x < nthr) ? (1u << j) : 0u;
-                    zb |= (x.y < nthr) ? (1u << j) : 0u;
-                    vr[j] = x.x * w.x;
-                    vi[j] = x.y * w.y;
-                }
+            for (int j = 0; j < 32; ++j) {
+                const float2 x = xp[lane + 32 * j];
+                const float2 w = s_win[lane + 32 * j];
+                ss = fmaf(x.x, x.x, ss);
+                ss = fmaf(x.y, x.y, ss);
+                // sign bit of (x + thr) <=> x < -thr; sample j ends up at bit 31 - j
+                za = __funnelshift_l(__float_as_uint(x.x + zthr), za, 1);
+                zb = __funnelshift_l(__float_as_uint(x.y + zthr), zb, 1);
+                vr[j] = x.x * w.x;
+                vi[j] = x.y * w.y;
+            }
+        }
+        int zc;
+        {
+            // pairs (2m, 2m+1) sit in one lane; pairs (2m+1, 2m+2) straddle to the next lane
+            unsigned zn = __shfl_sync(FULL, za, (lane + 1) & 31);
+            unsigned msk = FULL;
+            if (lane == 31) { zn <<= 1; msk = 0xfffffffeu; }
+            zc = __popc(za ^ zb) + __popc((zb ^ zn) & msk);
+            zc = warp_sum_i(zc);
+            if (zc_edge >= 0) zc = zc_edge;
+        }
+        ss = warp_sum(ss);
+        __syncwarp();                       // every lane has its samples: the buffer becomes scratch
+
+        // ---- phase 1: 32-point FFT over n1 (this lane holds z[lane + 32*n1])
+        fftreg::fft_dif<32>(vr, vi);
+
+        // ---- phase 2: inter-pass twiddle W_1024^(lane*k1)
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+            const float2 w = s_tw1[(k1 - 1) * 32 + lane];
+            const int p = pos32(k1);
+            const float xr = vr[p], xi = vi[p];
+            vr[p] = fmaf(xr, w.x, -(xi * w.y));
+            vi[p] = fmaf(xr, w.y, xi * w.x);
+        }
+
+        // ---- phase 3: 32x32 complex transpose through shared memory
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) sc2[lane * 33 + k1] = make_float2(vr[pos32(k1)], vi[pos32(k1)]);
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) { const float2 v = sc2[n2 * 33 + lane]; vr[n2] = v.x; vi[n2] = v.y; }
+        __syncwarp();
+
+        // ---- phase 4: 32-point FFT over n2; lane = k1, bin k = k1 + 32*k2 at pos32(k2)
+        fftreg::fft_dif<32>(vr, vi);
+
+        // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) and their
+        //      mirrors 1024-k (XOR-swizzled float2 buffer: conflict-free both ways)
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2)
+            sc2[32 * k2 + (lh ^ ((2 * k2) & 31))] = make_float2(vr[pos32(k2)], vi[pos32(k2)]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float2 v = sc2[base_lo ^ i]; vr[i] = v.x; vi[i] = v.y; }
+        { const float2 v = sc2[base_hi0]; vr[16] = v.x; vi[16] = v.y; }
+#pragma unroll
+        for (int i = 1; i < 16; ++i) { const float2 v = sc2[base_hi ^ (16 - i)]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
+        const float2 e512 = sc2[512];
+        __syncwarp();
+
+        // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
+        float m0l = 0.f, m1l = 0.f, m2l = 0.f, m0h = 0.f, m1h = 0.f, m2h = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float2 w = s_tw2[i * 32 + lane];
+            const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
+            const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
+            const float tx = fmaf(w.x, dx, -(w.y * dy));
+            const float ty = fmaf(w.x, dy, w.y * dx);
+            const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
+            const float pk = fmaf(ar, ar, ai * ai);
+            const float pm = fmaf(br, br, bi * bi);
+            const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
+            vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
+            const float d = float(i) - 7.5f;
+            m0l += sk; m1l = fmaf(d, sk, m1l); m2l = fmaf(d * d, sk, m2l);
+            m0h += sm; m1h = fmaf(-d, sm, m1h); m2h = fmaf(d * d, sm, m2h);
+        }
+        // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
+        const float p512 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
+        const float s512 = fast_sqrt(p512);
+
+        // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
+        const float kcl = 16.0f * lane + 7.5f;
+        const float kch = 1024.0f - 16.0f * lane - 7.5f;
+        float s0 = m0l + m0h;
+        float s1 = fmaf(kcl, m0l, m1l) + fmaf(kch, m0h, m1h);
+        if (lane == 31) { s0 += s512; s1 = fmaf(512.0f, s512, s1); }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;   // util.normalize tiny guard
+        const float cen = s1 / denom;                            // in bins
+        float q;
+        {
+            const float dl = kcl - cen, dh = kch - cen;
+            q = fmaf(dl * dl, m0l, fmaf(2.0f * dl, m1l, m2l)) +
+                fmaf(dh * dh, m0h, fmaf(2.0f * dh, m1h, m2h));
+            if (lane == 31) { const float dm = 512.0f - cen; q = fmaf(dm * dm, s512, q); }
+            q = warp_sum(q);
+        }
+        const float bw = sqrtf(fmaxf(q, 0.0f) / denom);
+
+        // ---- rolloff (librosa.feature.spectral_rolloff): first bin whose cumulative
+        //      magnitude reaches roll_percent * total
+        int rbin;
+        {
+            float pl = m0l;                       // inclusive scan, ascending lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float tv = __shfl_up_sync(FULL, pl, d);
+                if (lane >= d) pl += tv;
+            }
+            float ph = m0h;                       // inclusive scan, descending lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float tv = __shfl_down_sync(FULL, ph, d);
+                if (lane + d < 32) ph += tv;
+            }
+            const float tot_lo = __shfl_sync(FULL, pl, 31);
+            const float tot_hi = __shfl_sync(FULL, ph, 0);
+            const float mid = tot_lo + s512;      // s512 is warp-uniform (same smem word)
+            const float thr = a.roll_percent * (mid + tot_hi);
+            const unsigned lo_mask = __ballot_sync(FULL, pl >= thr);
+            if (lo_mask) {
+                const int tl = __ffs(lo_mask) - 1;
+                float cum = pl - m0l;
+                int cnt = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { cum += vi[i]; cnt += (cum < thr) ? 1 : 0; }
+                rbin = __shfl_sync(FULL, 16 * lane + min(cnt, 15), tl);
+            } else if (mid >= thr) {
+                rbin = 512;
             } else {
-                // edge frame (or odd alignment): mapped loads straight from global
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int s = fs + 2 * (lane + 32 * j);
-                    const float x0 = sample_padded(clip, a.n, s, a.pad_mode);
-                    const float x1 = sample_padded(clip, a.n, s + 1, a.pad_mode);
-                    const float e0 = sample_edge(clip, a.n, s);
-                    const float e1 = sample_edge(clip, a.n, s + 1);
-                    const float2 w = s_win[lane + 32 * j];
-                    ss = fmaf(x0, x0, ss);
-                    ss = fmaf(x1, x1, ss);
-                    za |= (e0 < nthr) ? (1u << j) : 0u;
-                    zb |= (e1 < nthr) ? (1u << j) : 0u;
-                    vr[j] = x0 * w.x;
-                    vi[j] = x1 * w.y;
-                }
-            }
-            // zero crossings: pairs (2m,2m+1) in-lane, pairs (2m+1,2m+2) with the next lane
-            int zc;
-            {
-                unsigned zn = __shfl_sync(FULL, za, (lane + 1) & 31);
-                unsigned msk = FULL;
-                if (lane == 31) { zn >>= 1; msk = 0x7fffffffu; }
-                zc = __popc(za ^ zb) + __popc((zb ^ zn) & msk);
-                zc = warp_sum_i(zc);
-            }
-            ss = warp_sum(ss);
-
-            // ---- phase 1: 32-point FFT over n1 (this lane holds z[lane + 32*n1])
-            fftreg::fft_dif<32>(vr, vi);
-
-            // ---- phase 2: inter-pass twiddle W_1024^(lane*k1)
-#pragma unroll
-            for (int k1 = 1; k1 < 32; ++k1) {
-                const float2 w = s_tw1[(k1 - 1) * 32 + lane];
-                const int p = pos32(k1);
-                const float xr = vr[p], xi = vi[p];
-                vr[p] = fmaf(xr, w.x, -(xi * w.y));
-                vi[p] = fmaf(xr, w.y, xi * w.x);
-            }
-
-            // ---- phase 3: 32x32 transpose through shared memory (re, then im)
-#pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) sc[lane * 33 + k1] = vr[pos32(k1)];
-            __syncwarp();
-#pragma unroll
-            for (int n2 = 0; n2 < 32; ++n2) vr[n2] = sc[n2 * 33 + lane];
-            __syncwarp();
-#pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) sc[lane * 33 + k1] = vi[pos32(k1)];
-            __syncwarp();
-#pragma unroll
-            for (int n2 = 0; n2 < 32; ++n2) vi[n2] = sc[n2 * 33 + lane];
-            __syncwarp();
-
-            // ---- phase 4: 32-point FFT over n2; lane = k1, bin k = k1 + 32*k2 at pos32(k2)
-            fftreg::fft_dif<32>(vr, vi);
-
-            // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) and their
-            //      mirrors 1024-k (XOR-swizzled buffer: conflict-free both ways)
-            const int hb = lane >> 4;
-            const int base_lo = (lane << 4) ^ lane;
-            const int base_hi0 = ((16 * (64 - lane)) & 1023) ^ ((64 - lane) & 31);
-            const int base_hi = ((63 - lane) << 4) ^ (31 - lane);
-            float e512r, e512i;
-#pragma unroll
-            for (int k2 = 0; k2 < 32; ++k2)
-                sc[32 * k2 + (lane ^ (((2 * k2) & 31) | hb))] = vr[pos32(k2)];
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) vr[i] = sc[base_lo ^ i];
-            vr[16] = sc[base_hi0];
-#pragma unroll
-            for (int i = 1; i < 16; ++i) vr[16 + i] = sc[base_hi ^ (16 - i)];
-            e512r = sc[512];
-            __syncwarp();
-#pragma unroll
-            for (int k2 = 0; k2 < 32; ++k2)
-                sc[32 * k2 + (lane ^ (((2 * k2) & 31) | hb))] = vi[pos32(k2)];
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) vi[i] = sc[base_lo ^ i];
-            vi[16] = sc[base_hi0];
-#pragma unroll
-            for (int i = 1; i < 16; ++i) vi[16 + i] = sc[base_hi ^ (16 - i)];
-            e512i = sc[512];
-            __syncwarp();
-
-            // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
-            float m0l = 0.f, m1l = 0.f, m2l = 0.f, m0h = 0.f, m1h = 0.f, m2h = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float2 w = s_tw2[i * 32 + lane];
-                const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
-                const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
-                const float tx = fmaf(w.x, dx, -(w.y * dy));
-                const float ty = fmaf(w.x, dy, w.y * dx);
-                const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
-                const float pk = fmaf(ar, ar, ai * ai);
-                const float pm = fmaf(br, br, bi * bi);
-                const float sk = sqrtf(pk), sm = sqrtf(pm);
-                vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
-                const float d = float(i) - 7.5f;
-                m0l += sk; m1l = fmaf(d, sk, m1l); m2l = fmaf(d * d, sk, m2l);
-                m0h += sm; m1h = fmaf(-d, sm, m1h); m2h = fmaf(d * d, sm, m2h);
-            }
-            // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
-            const float p512 = 4.0f * fmaf(e512r, e512r, e512i * e512i);
-            const float s512 = sqrtf(p512);
-
-            // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
-            const float kcl = 16.0f * lane + 7.5f;
-            const float kch = 1024.0f - 16.0f * lane - 7.5f;
-            float s0 = m0l + m0h;
-            float s1 = fmaf(kcl, m0l, m1l) + fmaf(kch, m0h, m1h);
-            if (lane == 31) { s0 += s512; s1 = fmaf(512.0f, s512, s1); }
-            s0 = warp_sum(s0);
-            s1 = warp_sum(s1);
-            const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;   // util.normalize tiny guard
-            const float cen = s1 / denom;                            // in bins
-            float q;
-            {
-                const float dl = kcl - cen, dh = kch - cen;
-                q = fmaf(dl * dl, m0l, fmaf(2.0f * dl, m1l, m2l)) +
-                    fmaf(dh * dh, m0h, fmaf(2.0f * dh, m1h, m2h));
-                if (lane == 31) { const float dm = 512.0f - cen; q = fmaf(dm * dm, s512, q); }
-                q = warp_sum(q);
-            }
-            const float bw = sqrtf(fmaxf(q, 0.0f) / denom);
-
-            // ---- rolloff (librosa.feature.spectral_rolloff): first bin whose cumulative
-            //      magnitude reaches roll_percent * total
-            int rbin;
-            {
-                float pl = m0l;                       // inclusive scan, ascending lanes
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const float tv = __shfl_up_sync(FULL, pl, d);
-                    if (lane >= d) pl += tv;
-                }
-                float ph = m0h;                       // inclusive scan, descending lanes
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const float tv = __shfl_down_sync(FULL, ph, d);
-                    if (lane + d < 32) ph += tv;
-                }
-                const float tot_lo = __shfl_sync(FULL, pl, 31);
-                const float tot_hi = __shfl_sync(FULL, ph, 0);
-                const float mid = tot_lo + s512;      // s512 is warp-uniform (same smem word)
-                const float thr = a.roll_percent * (mid + tot_hi);
-                const unsigned lo_mask = __ballot_sync(FULL, pl >= thr);
-                if (lo_mask) {
-                    const int tl = __ffs(lo_mask) - 1;
-                    float cum = pl - m0l;
+                const unsigned hi_mask = __ballot_sync(FULL, mid + ph >= thr);
+                if (hi_mask) {
+                    const int tl = 31 - __clz(hi_mask);
+                    float cum = mid + (ph - m0h);
                     int cnt = 0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { cum += vi[i]; cnt += (cum < thr) ? 1 : 0; }
-                    rbin = __shfl_sync(FULL, 16 * lane + min(cnt, 15), tl);
-                } else if (mid >= thr) {
-                    rbin = 512;
+                    for (int i = 15; i >= 0; --i) { cum += vi[16 + i]; cnt += (cum < thr) ? 1 : 0; }
+                    // ascending bins are i = 15..0: the cnt-th of them is i = 15 - cnt
+                    rbin = __shfl_sync(FULL, 1024 - 16 * lane - (15 - min(cnt, 15)), tl);
                 } else {
-                    const unsigned hi_mask = __ballot_sync(FULL, mid + ph >= thr);
-                    if (hi_mask) {
-                        const int tl = 31 - __clz(hi_mask);
-                        float cum = mid + (ph - m0h);
-                        int cnt = 0;
-#pragma unroll
-                        for (int i = 15; i >= 0; --i) { cum += vi[16 + i]; cnt += (cum < thr) ? 1 : 0; }
-                        // ascending bins are i = 15..0: cnt-th of them is i = 15 - cnt
-                        rbin = __shfl_sync(FULL, 1024 - 16 * lane - (15 - min(cnt, 15)), tl);
-                    } else {
-                        rbin = 1024;
-                    }
+                    rbin = 1024;
                 }
-            }
-
-            // ---- phase 7: power (or magnitude) spectrum -> padded scratch, q(k) = k + k/16
-            if (a.use_mag) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vi[i];
-                sc[17 * (64 - lane)] = vi[16];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vi[16 + i];
-                if (lane == 31) sc[544] = s512;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vr[i];
-                sc[17 * (64 - lane)] = vr[16];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vr[16 + i];
-                if (lane == 31) sc[544] = p512;
-            }
-            sc[17 * lane + 16] = 0.0f;
-            sc[17 * (63 - lane) + 16] = 0.0f;
-            __syncwarp();
-
-            // ---- phase 8: banded mel projection (librosa.feature.melspectrogram's einsum)
-            float wmax = 0.0f;
-            if (a.mel_out != nullptr) {
-                for (int g = 0; g < ft.n_groups; ++g) {
-                    const int gmax = s_meta[g];
-                    const float* wp = s_melw + s_meta[kMaxMelGroups + g] + lane;
-                    const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * g + lane];
-                    float acc = 0.0f;
-#pragma unroll 4
-                    for (int i = 0; i < gmax; ++i) acc = fmaf(wp[32 * i], pp[i], acc);
-                    const int m = 32 * g + lane;
-                    if (m < a.n_mels) stage[m * (NW + 1) + warp] = acc;
-                    wmax = fmaxf(wmax, acc);
-                }
-                wmax = warp_max(wmax);
-            }
-            __syncwarp();   // scratch is reused by the next frame's transposes
-
-            if (lane == 0) {
-                sstage[0 * NW + warp] = cen * a.binhz;
-                sstage[1 * NW + warp] = bw * a.binhz;
-                sstage[2 * NW + warp] = float(rbin) * a.binhz;
-                sstage[3 * NW + warp] = float(zc) * (1.0f / float(kFastNfft));
-                sstage[4 * NW + warp] = sqrtf(ss * (1.0f / float(kFastNfft)));
-                if (a.mel_out != nullptr) atomicMax(&tilemax[buf], __float_as_int(wmax));
-                // librosa.util.valid_audio: a non-finite sample poisons the sum of squares
-                if (a.status != nullptr && !(fabsf(ss) <= 3.0e38f)) atomicOr(a.status + b, 1);
             }
         }
-        __syncthreads();
 
-        // ---- flush the tile: rows of nf consecutive frames per mel band
+        // ---- phase 7: power (or magnitude) spectrum -> padded scratch, q(k) = k + k/16
+        if (a.use_mag) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vi[i];
+            sc[17 * (64 - lane)] = vi[16];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vi[16 + i];
+            if (lane == 31) sc[544] = s512;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vr[i];
+            sc[17 * (64 - lane)] = vr[16];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vr[16 + i];
+            if (lane == 31) sc[544] = p512;
+        }
+        sc[17 * lane + 16] = 0.0f;
+        sc[17 * (63 - lane) + 16] = 0.0f;
+        if (lane < 16) sc[1089 + lane] = 0.0f;    // zero-weight taps past bin 1024 must read finite values
+        __syncwarp();
+
+        // ---- phase 8: banded mel projection (librosa.feature.melspectrogram's einsum);
+        //      start offsets were shifted on the host so that the 32 lanes hit 32 banks
         if (a.mel_out != nullptr) {
-            float* outb = a.mel_out + (size_t)b * a.n_mels * a.T + t0;
-            for (int idx = tid; idx < a.n_mels * NW; idx += NT) {
-                const int m = idx / NW, j = idx - m * NW;
-                if (j < nf) outb[(size_t)m * a.T + j] = stage[m * (NW + 1) + j];
+            float wmax = 0.0f;
+            float* outb = a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+            for (int g = 0; g < ft.n_groups; ++g) {
+                const int n4 = s_meta[g];
+                const float4* wp = reinterpret_cast<const float4*>(s_melw + s_meta[kMaxMelGroups + g]) + lane;
+                const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * g + lane];
+                float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 2
+                for (int i4 = 0; i4 < n4; ++i4) {
+                    const float4 w = wp[32 * i4];
+                    a0 = fmaf(w.x, pp[4 * i4 + 0], a0);
+                    a1 = fmaf(w.y, pp[4 * i4 + 1], a1);
+                    a0 = fmaf(w.z, pp[4 * i4 + 2], a0);
+                    a1 = fmaf(w.w, pp[4 * i4 + 3], a1);
+                }
+                const float acc = a0 + a1;
+                const int m = 32 * g + lane;
+                if (m < a.n_mels) outb[(size_t)m * a.T] = acc;
+                wmax = fmaxf(wmax, acc);
             }
+            clip_max = fmaxf(clip_max, wmax);
         }
-        if (a.stats != nullptr && tid < 5 * NW) {
-            const int s = tid / NW, j = tid - s * NW;
-            if (j < nf) a.stats[((size_t)b * 5 + s) * a.T + t0 + j] = sstage[s * NW + j];
+        if (lane == 0) {
+            if (a.stats != nullptr) {
+                float* st = a.stats + (size_t)b * 5 * a.T + t;
+                st[0] = cen * a.binhz;
+                st[(size_t)a.T] = bw * a.binhz;
+                st[(size_t)2 * a.T] = float(rbin) * a.binhz;
+                st[(size_t)3 * a.T] = float(zc) * (1.0f / float(kFastNfft));
+                st[(size_t)4 * a.T] = sqrtf(ss * (1.0f / float(kFastNfft)));
+            }
+            // librosa.util.valid_audio: a non-finite sample poisons the sum of squares
+            if (a.status != nullptr && !(fabsf(ss) <= 3.0e38f)) atomicOr(a.status + b, 1);
         }
-        if (tid == 0 && a.clipmax != nullptr) {
-            const int v = tilemax[buf];
-            tilemax[buf] = 0;
-            atomicMax(reinterpret_cast<int*>(a.clipmax) + b, v);
+        // ---- next frame; flush the running mel maximum when the clip (or this warp's run) ends
+        const bool last = (t == a.T - 1) || (g + 1 == g1);
+        if (last && a.clipmax != nullptr && a.mel_out != nullptr) {
+            const float m = warp_max(clip_max);
+            if (lane == 0) atomicMax(reinterpret_cast<int*>(a.clipmax) + b, __float_as_int(m));
+            clip_max = 0.0f;
         }
+        if (++t == a.T) { t = 0; ++b; }
+        __syncwarp();                       // scratch reads are done before the next frame lands
     }
 }
 
@@ -508,25 +469,22 @@ static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, con
     cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    const long long items = (long long)a.B * ((a.T + NW - 1) / NW);
-    const int grid = (int)((items < num_sms) ? items : num_sms);
-    if (grid <= 0) return cudaSuccess;
-    frames_fast_2048<NW><<<grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    const long long frames = (long long)a.B * a.T;
+    if (frames <= 0) return cudaSuccess;
+    long long grid = (frames + NW - 1) / NW;
+    if (grid > num_sms) grid = num_sms;
+    frames_fast_2048<NW><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                int num_sms, cudaStream_t stream) {
-    int nw = pick_fast_warps(a.T);
-    // fall back to fewer warps if the shared-memory budget (227 KB) is exceeded
-    while (nw > 8 && fast_smem_bytes(ft, nw, a.n_fft, a.hop, a.n_mels) > 227 * 1024) nw -= 4;
-    if (fast_smem_bytes(ft, nw, a.n_fft, a.hop, a.n_mels) > 227 * 1024) return cudaErrorInvalidValue;
-    switch (nw) {
-        case 16: return launch_fast_nw<16>(a, d_tables, ft, num_sms, stream);
-        case 12: return launch_fast_nw<12>(a, d_tables, ft, num_sms, stream);
-        default: return launch_fast_nw<8>(a, d_tables, ft, num_sms, stream);
-    }
+    if (fast_smem_bytes(ft, 16, a.n_fft, a.hop, a.n_mels) <= 227 * 1024)
+        return launch_fast_nw<16>(a, d_tables, ft, num_sms, stream);
+    if (fast_smem_bytes(ft, 8, a.n_fft, a.hop, a.n_mels) <= 227 * 1024)
+        return launch_fast_nw<8>(a, d_tables, ft, num_sms, stream);
+    return cudaErrorInvalidValue;
 }
 
 // ---------------------------------------------------------------------------
