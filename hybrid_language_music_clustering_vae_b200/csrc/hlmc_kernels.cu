@@ -114,7 +114,7 @@ __device__ __forceinline__ float sample_edge(const float* __restrict__ clip, int
 // then the scratch for the FFT transposes and the mel gather.  There is no
 // CTA-wide barrier after setup.
 // ---------------------------------------------------------------------------
-constexpr int kWarpBufFloats = 2 * 32 * 33 + 8;   // 32x33 float2 transpose tile (+ slack) = 2120
+constexpr int kWarpBufFloats = 2 * (1024 + 64 + 1) + 2;   // padded 1024-bin complex spectrum (>= 32x33 transpose tile)
 
 __host__ __device__ constexpr int pos32(int k) { return fftreg::fft_pos<32>(k); }
 
@@ -138,7 +138,7 @@ int pick_fast_warps(int T) { (void)T; return 16; }
 
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -186,12 +186,12 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     float clip_max = 0.0f;
     const float zthr = a.zcr_thr;
 
-    // per-lane constants of the XOR-swizzled regroup (float2 units)
-    const int hb = lane >> 4;
-    const int lh = lane ^ hb;
-    const int base_lo = (lane << 4) ^ lane;
-    const int base_hi0 = ((16 * (64 - lane)) & 1023) ^ ((64 - lane) & 31);
-    const int base_hi = ((63 - lane) << 4) ^ (31 - lane);
+    // per-lane bases of the regroup buffer, layout p(k) = k + k/16 in float2 units: every
+    // access below is base + immediate and conflict-free (17 is odd)
+    const int zw_base = lane + (lane >> 4);              // write: k = lane + 32*k2 -> zw_base + 34*k2
+    const int zlo_base = 17 * lane;                      // read:  k = 16*lane + i  -> zlo_base + i
+    const int zhi_base = 17 * (63 - lane) + 16;          // read:  k = 1024-16*lane-i (i>=1) -> zhi_base - i
+    const int zhi0 = (lane == 0) ? 0 : 17 * (64 - lane); // read:  k = (1024-16*lane) mod 1024
 
     for (long long g = g0; g < g1; ++g) {
         const float* clip = a.wave + (long long)b * a.pitch;
@@ -291,17 +291,17 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         fftreg::fft_dif<32>(vr, vi);
 
         // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) and their
-        //      mirrors 1024-k (XOR-swizzled float2 buffer: conflict-free both ways)
+        //      mirrors 1024-k
 #pragma unroll
         for (int k2 = 0; k2 < 32; ++k2)
-            sc2[32 * k2 + (lh ^ ((2 * k2) & 31))] = make_float2(vr[pos32(k2)], vi[pos32(k2)]);
+            sc2[zw_base + 34 * k2] = make_float2(vr[pos32(k2)], vi[pos32(k2)]);
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const float2 v = sc2[base_lo ^ i]; vr[i] = v.x; vi[i] = v.y; }
-        { const float2 v = sc2[base_hi0]; vr[16] = v.x; vi[16] = v.y; }
+        for (int i = 0; i < 16; ++i) { const float2 v = sc2[zlo_base + i]; vr[i] = v.x; vi[i] = v.y; }
+        { const float2 v = sc2[zhi0]; vr[16] = v.x; vi[16] = v.y; }
 #pragma unroll
-        for (int i = 1; i < 16; ++i) { const float2 v = sc2[base_hi ^ (16 - i)]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
-        const float2 e512 = sc2[512];
+        for (int i = 1; i < 16; ++i) { const float2 v = sc2[zhi_base - i]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
+        const float2 e512 = sc2[544];
         __syncwarp();
 
         // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
@@ -422,15 +422,27 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 const int n4 = s_meta[g];
                 const float4* wp = reinterpret_cast<const float4*>(s_melw + s_meta[kMaxMelGroups + g]) + lane;
                 const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * g + lane];
-                float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll 2
-                for (int i4 = 0; i4 < n4; ++i4) {
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                int i4 = 0;
+                for (; i4 + 2 <= n4; i4 += 2) {
+                    const float4 w = wp[32 * i4], v = wp[32 * i4 + 32];
+                    a0 = fmaf(w.x, pp[4 * i4 + 0], a0);
+                    a1 = fmaf(w.y, pp[4 * i4 + 1], a1);
+                    a2 = fmaf(w.z, pp[4 * i4 + 2], a2);
+                    a3 = fmaf(w.w, pp[4 * i4 + 3], a3);
+                    a0 = fmaf(v.x, pp[4 * i4 + 4], a0);
+                    a1 = fmaf(v.y, pp[4 * i4 + 5], a1);
+                    a2 = fmaf(v.z, pp[4 * i4 + 6], a2);
+                    a3 = fmaf(v.w, pp[4 * i4 + 7], a3);
+                }
+                if (i4 < n4) {
                     const float4 w = wp[32 * i4];
                     a0 = fmaf(w.x, pp[4 * i4 + 0], a0);
                     a1 = fmaf(w.y, pp[4 * i4 + 1], a1);
-                    a0 = fmaf(w.z, pp[4 * i4 + 2], a0);
-                    a1 = fmaf(w.w, pp[4 * i4 + 3], a1);
+                    a2 = fmaf(w.z, pp[4 * i4 + 2], a2);
+                    a3 = fmaf(w.w, pp[4 * i4 + 3], a3);
                 }
+                a0 += a2; a1 += a3;
                 const float acc = a0 + a1;
                 const int m = 32 * g + lane;
                 if (m < a.n_mels) outb[(size_t)m * a.T] = acc;
