@@ -12,13 +12,14 @@ REL_TOL = 1e-4            # MFCC and statistics: <= 1e-4 of the clip's max |refe
 
 def oracle_clip(y, *, sr=22050, n_fft=2048, hop_length=512, n_mels=128, n_mfcc=40, pad_mode="constant",
                 center=True, win_length=None, window="hann", ref=np.max, top_db=80.0, power=2.0,
-                roll_percent=0.85):
+                roll_percent=0.85, **mel_kw):
+    """`mel_kw`: htk / fmin / fmax / norm of librosa.filters.mel."""
     kw = dict(n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window, center=center,
               pad_mode=pad_mode)
-    mel = orc.melspectrogram(y=y, sr=sr, n_mels=n_mels, power=power, **kw)
+    mel = orc.melspectrogram(y=y, sr=sr, n_mels=n_mels, power=power, **kw, **mel_kw)
     out = {"mel": mel, "logmel": orc.power_to_db(mel, ref=ref, top_db=top_db)}
     if n_mfcc:
-        out["mfcc"] = orc.mfcc(y=y, sr=sr, n_mfcc=n_mfcc, n_mels=n_mels, **kw)
+        out["mfcc"] = orc.mfcc(y=y, sr=sr, n_mfcc=n_mfcc, n_mels=n_mels, power=power, **kw, **mel_kw)
     S = np.abs(orc.stft(y, **kw))
     out["S"] = S
     stats = np.empty((5, mel.shape[-1]), np.float64)

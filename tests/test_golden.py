@@ -1,0 +1,55 @@
+"""Golden fixtures: oracle drift guard + independent cross-check (CPU), CUDA parity (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import slow_exact as sx
+from parity import oracle_clip, compare_clip, assert_clip
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+KW = {
+    "a": dict(n_fft=2048, hop_length=512, n_mels=128, n_mfcc=40, pad_mode="constant"),
+    "b": dict(n_fft=512, hop_length=128, n_mels=40, n_mfcc=13, pad_mode="reflect"),
+}
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_oracle_reproduces_golden(case):
+    y = G[f"{case}_y"]
+    for i in range(len(y)):
+        r = oracle_clip(y[i], **KW[case])
+        assert np.array_equal(r["logmel"], G[f"{case}_logmel"][i])
+        assert np.array_equal(r["mfcc"], G[f"{case}_mfcc"][i])
+        assert np.array_equal(r["stats"], G[f"{case}_stats"][i])
+
+
+def test_golden_matches_direct_dft():
+    y = G["b_y"]
+    for i in range(len(y)):
+        ref = sx.features(y[i], 22050, 512, 128, 40, 13, "reflect")
+        assert np.abs(G["b_logmel"][i] - ref["logmel"]).max() < 2e-3
+        assert np.abs(G["b_mfcc"][i] - ref["mfcc"]).max() <= 1e-4 * np.abs(ref["mfcc"]).max()
+        st = G["b_stats"][i]
+        for j in (0, 1, 4):
+            assert np.allclose(st[j], ref["stats"][j], rtol=2e-5, atol=1e-9)
+        assert np.array_equal(st[3], ref["stats"][3])
+        assert np.allclose(st[2], ref["stats"][2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_cuda_matches_golden(case, built):
+    import torch
+
+    hl = built
+    kw = KW[case]
+    ex = hl.FeatureExtractor(ref=np.max, **kw)
+    y = G[f"{case}_y"]
+    out = ex.extract_device(torch.from_numpy(y).cuda())
+    torch.cuda.synchronize()
+    for i in range(len(y)):
+        want = oracle_clip(y[i], **kw)   # for the rolloff tie rule only
+        want.update(logmel=G[f"{case}_logmel"][i], mfcc=G[f"{case}_mfcc"][i], stats=G[f"{case}_stats"][i])
+        got = {k: out[k][i].cpu().numpy() for k in ("logmel", "mfcc", "stats")}
+        assert_clip(compare_clip(got, want, n_fft=kw["n_fft"]), where=f"golden {case}[{i}]")

@@ -1,0 +1,333 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle; needs a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import librosa_oracle as orc
+from parity import oracle_clip, compare_clip, assert_clip, LOGMEL_TOL_DB, REL_TOL
+
+pytestmark = pytest.mark.gpu
+SR = 22050
+
+
+def _run(hl, y, generic=False, pitch=None, **kw):
+    import torch
+
+    ex = hl.FeatureExtractor(ref=np.max, **kw)
+    if generic:
+        ex.force_generic(True)
+    if pitch is None:
+        d = torch.from_numpy(y).cuda()
+    else:
+        store = torch.zeros((y.shape[0], pitch), dtype=torch.float32, device="cuda")
+        store[:, : y.shape[1]] = torch.from_numpy(y).cuda()
+        d = store[:, : y.shape[1]]
+    out = ex.extract_device(d)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    ex.close()
+    return res
+
+
+def _check_batch(hl, y, generic=False, pitch=None, **kw):
+    res = _run(hl, y, generic=generic, pitch=pitch, **kw)
+    okw = {k: v for k, v in kw.items()}
+    okw.setdefault("n_mfcc", 20)
+    flips = 0
+    for i in range(y.shape[0]):
+        want = oracle_clip(y[i], **okw)
+        got = {k: res[k][i] for k in ("logmel", "mfcc", "stats") if k in res}
+        m = compare_clip(got, want, n_fft=kw.get("n_fft", 2048), roll_percent=kw.get("roll_percent", 0.85))
+        assert_clip(m, where=f"clip {i} {kw} generic={generic}")
+        flips += m.get("rolloff_flips", 0)
+    frames = y.shape[0] * res["logmel"].shape[-1]
+    assert flips <= max(2, frames // 200), f"too many rolloff tie flips: {flips}/{frames}"
+    assert not res["status"].any()
+    return res
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_mixture_3s_full_set(built, generic):
+    """configs[0]-shaped: 3 s clips, the 1_preprocessing.py feature set."""
+    y = built.synth.synth_batch(40, 66150, seed=20260)
+    res = _check_batch(built, y, generic=generic, n_mfcc=40)
+    assert res["logmel"].shape == (40, 128, 130) and res["mfcc"].shape == (40, 40, 130)
+    assert res["stats"].shape == (40, 5, 130)
+
+
+def test_30s_clips(built):
+    """GTZAN-shaped (configs[2]): 30 s clips, T = 1292."""
+    y = built.synth.synth_batch(3, 661500, seed=20262)
+    res = _check_batch(built, y, n_mfcc=40)
+    assert res["logmel"].shape == (3, 128, 1292)
+
+
+@pytest.mark.parametrize("pad_mode", ["constant", "reflect", "edge"])
+@pytest.mark.parametrize("generic", [False, True])
+def test_pad_modes(built, pad_mode, generic):
+    y = built.synth.synth_batch(6, 9000, seed=3)
+    _check_batch(built, y, generic=generic, pad_mode=pad_mode, n_mfcc=13)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_center_false(built, generic):
+    y = built.synth.synth_batch(4, 10000, seed=4)
+    res = _check_batch(built, y, generic=generic, center=False, n_mfcc=13)
+    assert res["logmel"].shape[-1] == 1 + (10000 - 2048) // 512
+
+
+@pytest.mark.parametrize("n", [1, 2, 511, 1025, 2047, 2048, 2049, 4097])
+@pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
+def test_ragged_lengths(built, n, pad_mode):
+    """Frame counts and values for clips shorter than / around one frame."""
+    y = (0.1 * np.random.default_rng(n).standard_normal((3, n))).astype(np.float32)
+    res = _check_batch(built, y, pad_mode=pad_mode, n_mfcc=13)
+    assert res["logmel"].shape[-1] == 1 + n // 512
+
+
+@pytest.mark.parametrize("pitch_extra", [0, 1, 2, 3, 5])
+def test_row_pitch_and_misalignment(built, pitch_extra):
+    """Rows that are not 16-byte aligned (TMA needs the shifted-landing path) and odd pitches."""
+    n = 8191
+    y = built.synth.synth_batch(5, n, seed=9)
+    _check_batch(built, y, pitch=n + pitch_extra, n_mfcc=13)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(512, 128), (1024, 256), (4096, 1024), (256, 64), (8192, 2048)])
+def test_n_fft_sweep(built, n_fft, hop):
+    """configs[4]'s FFT sizes; n_fft=512/256 with 128 mels has empty filters and must not crash."""
+    y = built.synth.synth_batch(4, 30000, seed=n_fft)
+    _check_batch(built, y, n_fft=n_fft, hop_length=hop, n_mfcc=20)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_mels=64, n_mfcc=20), dict(n_mels=40, n_mfcc=13, htk=True), dict(fmin=100.0, fmax=8000.0),
+    dict(win_length=1024), dict(window="hamming"), dict(window=("kaiser", 8.0)), dict(hop_length=300),
+    dict(hop_length=1000, n_mfcc=12), dict(n_mels=200, n_mfcc=40), dict(norm=None), dict(roll_percent=0.5),
+])
+@pytest.mark.parametrize("generic", [False, True])
+def test_parameter_coverage(built, kw, generic):
+    y = built.synth.synth_batch(4, 12000, seed=17)
+    _check_batch(built, y, generic=generic, **kw)
+
+
+def test_power_one_and_db_options(built):
+    import torch
+
+    hl = built
+    y = hl.synth.synth_batch(4, 12000, seed=21)
+    for ref, top_db, amin in ((1.0, 80.0, 1e-10), (np.max, None, 1e-10), (0.5, 40.0, 1e-6)):
+        ex = hl.FeatureExtractor(power=1.0, ref=ref, top_db=top_db, amin=amin, n_mfcc=13, lifter=22)
+        out = ex.extract_device(torch.from_numpy(y).cuda())
+        for i in range(len(y)):
+            mel = orc.melspectrogram(y=y[i], sr=SR, power=1.0)
+            want = orc.power_to_db(mel, ref=ref, top_db=top_db, amin=amin)
+            assert np.abs(out["logmel"][i].cpu().numpy() - want).max() <= LOGMEL_TOL_DB
+            mf = orc.mfcc(y=y[i], sr=SR, n_mfcc=13, lifter=22, power=1.0)
+            assert np.abs(out["mfcc"][i].cpu().numpy() - mf).max() <= REL_TOL * np.abs(mf).max()
+
+
+def test_plan_tables_match_oracle(built):
+    import scipy.fftpack
+
+    ex = built.FeatureExtractor(n_mfcc=40)
+    assert np.abs(ex.mel_basis() - orc.mel(sr=SR, n_fft=2048)).max() < 1e-7
+    D = scipy.fftpack.dct(np.eye(128, dtype=np.float64), axis=0, type=2, norm="ortho")[:40]
+    assert np.abs(ex.dct_basis() - D).max() < 1e-7
+    ex2 = built.FeatureExtractor(n_mels=40, htk=True, fmin=50.0, fmax=7000.0, n_fft=1024, n_mfcc=0)
+    assert np.abs(ex2.mel_basis() - orc.mel(sr=SR, n_fft=1024, n_mels=40, htk=True, fmin=50.0, fmax=7000.0)).max() < 1e-7
+
+
+def test_nonfinite_clips_are_flagged_not_fatal(built):
+    """[R] 1_preprocessing.py:248-251: a bad file is skipped, the rest of the batch is unaffected."""
+    import torch
+
+    hl = built
+    y = hl.synth.synth_batch(6, 20000, seed=5)
+    clean = _run(hl, y, n_mfcc=13)
+    bad = y.copy()
+    bad[1, 777] = np.nan
+    bad[4, 19999] = np.inf
+    res = _run(hl, bad, n_mfcc=13)
+    assert res["status"].tolist() == [0, 1, 0, 0, 1, 0]
+    for i in (0, 2, 3, 5):
+        for k in ("logmel", "mfcc", "stats"):
+            assert np.array_equal(res[k][i], clean[k][i]), (k, i)
+    with pytest.raises(hl.ParameterError):
+        hl.feature.melspectrogram(y=bad[1])
+    with pytest.raises(hl.ParameterError):
+        hl.preprocessing.extract_all_features(bad[4], SR)
+
+
+def test_host_pipeline_equals_device_path(built):
+    import torch
+
+    hl = built
+    y = hl.synth.synth_batch(37, 22050, seed=8)
+    ex = hl.FeatureExtractor(ref=np.max, n_mfcc=40)
+    dev = ex.extract_device(torch.from_numpy(y).cuda(), pooled=True)
+    torch.cuda.synchronize()
+    for chunk, streams in ((0, 3), (5, 2), (37, 1), (1, 4)):
+        host = ex.extract_host(y, pooled=True, chunk_clips=chunk, n_streams=streams)
+        for k in ("logmel", "mfcc", "stats", "status", "pooled"):
+            assert np.array_equal(host[k], dev[k].cpu().numpy()), (k, chunk, streams)
+        h2d, d2h = ex.last_transfer_bytes()
+        assert h2d == y.nbytes and d2h == sum(host[k].nbytes for k in ("logmel", "mfcc", "stats", "status", "pooled"))
+    # strided host input (row pitch > n)
+    wide = np.zeros((37, 22050 + 7), np.float32)
+    wide[:, :22050] = y
+    host = ex.extract_host(wide[:, :22050])
+    assert np.array_equal(host["logmel"], dev["logmel"].cpu().numpy())
+    # pooled columns = np.mean / np.std over frames, in the scripts' order
+    lm, mf, st = host["logmel"], host["mfcc"], host["stats"]
+    want = np.concatenate([lm.mean(-1), lm.std(-1), mf.mean(-1), mf.std(-1),
+                           np.stack([st.mean(-1), st.std(-1)], axis=-1).reshape(len(y), 10)], axis=1)
+    got = dev["pooled"].cpu().numpy()
+    assert got.shape == (37, 346)
+    assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max()
+
+
+def test_multi_gpu_thread_sharding_single_device(built):
+    """extract_multi_gpu with the one visible device twice: shards meet in host memory, no collective."""
+    hl = built
+    y = hl.synth.synth_batch(11, 22050, seed=12)
+    ref = hl.FeatureExtractor(ref=np.max, n_mfcc=40).extract_host(y)
+    out = hl.sharding.extract_multi_gpu(y, [0, 0], dict(ref=np.max, n_mfcc=40))
+    for k in ("logmel", "mfcc", "stats", "status"):
+        assert np.array_equal(out[k], ref[k]), k
+
+
+def test_librosa_compatible_functions(built):
+    """Each librosa call the scripts make, by its own name and signature."""
+    import torch
+
+    hl = built
+    y = hl.synth.synth_batch(3, 22050, seed=30)[1]
+    D = hl.stft(y)
+    Do = orc.stft(y)
+    assert D.shape == Do.shape and D.dtype == np.complex64
+    assert np.abs(D - Do).max() <= 2e-6 * np.abs(Do).max()
+    mel = hl.feature.melspectrogram(y=y, sr=SR, n_mels=128, n_fft=2048, hop_length=512)
+    melo = orc.melspectrogram(y=y, sr=SR)
+    assert mel.dtype == np.float32 and np.abs(mel - melo).max() <= 1e-5 * melo.max()
+    db = hl.power_to_db(mel, ref=np.max)
+    assert np.abs(db - orc.power_to_db(melo, ref=np.max)).max() <= LOGMEL_TOL_DB and db.max() == 0.0
+    mf = hl.feature.mfcc(y=y, sr=SR, n_mfcc=40, n_fft=2048, hop_length=512)
+    mfo = orc.mfcc(y=y, sr=SR, n_mfcc=40)
+    assert mf.shape == (40, 44) and np.abs(mf - mfo).max() <= REL_TOL * np.abs(mfo).max()
+    for name in ("spectral_centroid", "spectral_bandwidth"):
+        got = getattr(hl.feature, name)(y=y, sr=SR, hop_length=512)
+        want = getattr(orc, name)(y=y, sr=SR, hop_length=512)
+        assert got.shape == want.shape == (1, 44) and got.dtype == np.float64
+        assert np.abs(got - want).max() <= REL_TOL * np.abs(want).max()
+    ro = hl.feature.spectral_rolloff(y=y, sr=SR, hop_length=512)
+    assert np.mean(np.abs(ro - orc.spectral_rolloff(y=y, sr=SR)) < 1e-3) >= 0.95
+    z = hl.feature.zero_crossing_rate(y, hop_length=512)
+    assert np.array_equal(z, orc.zero_crossing_rate(y, hop_length=512)) and z.dtype == np.float64
+    r = hl.feature.rms(y=y, hop_length=512)
+    ro_ = orc.rms(y=y, hop_length=512)
+    assert r.dtype == np.float32 and np.abs(r - ro_).max() <= REL_TOL * ro_.max()
+    # batched leading dimension and CUDA tensors
+    yb = hl.synth.synth_batch(3, 22050, seed=30)
+    mb = hl.feature.melspectrogram(y=yb, sr=SR)
+    assert mb.shape == (3, 128, 44) and np.array_equal(mb[1], mel)
+    mc = hl.feature.melspectrogram(y=torch.from_numpy(yb).cuda(), sr=SR)
+    assert mc.is_cuda and np.array_equal(mc.cpu().numpy(), mb)
+    # per-clip ref=max for batched power_to_db
+    dbb = hl.power_to_db(mb, ref=np.max)
+    assert np.array_equal(dbb[1], db) and all(dbb[i].max() == 0.0 for i in range(3))
+
+
+def test_script_level_functions_and_layout(built, tmp_path):
+    hl = built
+    pp = hl.preprocessing
+    y = hl.synth.synth_batch(5, 66150, seed=40)
+    # 1_preprocessing.py
+    lm = pp.extract_mel_spectrogram(y[0], SR)
+    assert np.abs(lm - orc.basic_extract_mel_spectrogram(y[0], SR)).max() <= LOGMEL_TOL_DB
+    mf = pp.extract_mfcc(y[0], SR)
+    assert np.abs(mf - orc.basic_extract_mfcc(y[0], SR)).max() <= REL_TOL * np.abs(mf).max()
+    sp = pp.extract_spectral_features(y[0], SR)
+    assert list(sp) == ["spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "zcr", "rms"]
+    assert sp["spectral_centroid"].shape == (1, 130) and sp["rms"].dtype == np.float32
+    f = pp.extract_all_features(y[0], SR)
+    want = orc.extract_all_features(y[0], SR, with_chroma=False)
+    assert f.shape == (370,) and f.dtype == np.float64
+    # pooled means / stds of quantities that each meet the per-frame tolerance; the two
+    # rolloff columns may move by a tie flip (one 10.77 Hz bin in one of 130 frames)
+    d = np.abs(f[:346] - want)
+    tol = 1e-3 + 1e-4 * np.abs(want)
+    tol[340:342] = 3 * (SR / 2048)
+    assert np.all(d <= tol), np.nonzero(d > tol)
+    assert np.all(f[346:] == 0.0)        # chroma policy "zeros", logged
+    fb = pp.extract_all_features_batch(y, SR, chroma="nan")
+    assert fb.shape == (5, 370) and np.isnan(fb[:, 346:]).all() and np.array_equal(fb[0, :346], f[:346])
+    # 1_preprocessing_advanced.py
+    mel, flat, status = pp.process_batch_advanced(y, SR)
+    assert mel.shape == (5, 128, 1024) and mel.dtype == np.float32 and flat.shape == (5, 290)
+    want_mel = orc.adv_extract_mel_spectrogram(y[2], SR)
+    assert np.abs(mel[2] - want_mel).max() <= LOGMEL_TOL_DB       # T=130 -> right-padded with the clip minimum
+    long = np.zeros((2, 661500), np.float32)
+    long[:, :66150] = y[:2]
+    mel_l, flat_l, _ = pp.process_batch_advanced(long, SR)
+    assert np.abs(mel_l[1] - orc.adv_extract_mel_spectrogram(long[1], SR)).max() <= LOGMEL_TOL_DB   # T=1292 -> crop
+    wantf = orc.extract_flattened_features(long[1], SR, with_chroma=False)
+    assert np.abs(flat_l[1, :266] - wantf).max() <= 2e-3 * max(1.0, np.abs(wantf).max())
+    # on-disk layout
+    labels = np.array(["a", "b", "a", "b", "a"])
+    raw, norm = pp.save_processed_data1(str(tmp_path / "p1"), fb, labels)
+    assert np.load(tmp_path / "p1" / "features_raw.npy").shape == (5, 370)
+    assert np.load(tmp_path / "p1" / "features_normalized.npy").dtype == np.float64
+    for name in ("labels.npy", "scaler.pkl", "imputer.pkl", "config.pkl"):
+        assert (tmp_path / "p1" / name).exists()
+    pp.save_processed_data2(str(tmp_path / "p2"), mel, flat, labels, lyrics_embeddings=np.zeros((5, 768), np.float32))
+    assert np.load(tmp_path / "p2" / "mel_spectrograms_normalized.npy").shape == (5, 128, 1024)
+    assert np.load(tmp_path / "p2" / "mel_spectrograms_raw.npy").dtype == np.float32
+    assert np.load(tmp_path / "p2" / "features_raw.npy").shape == (5, 290)
+    for name in ("mel_scaler.pkl", "flat_scaler.pkl", "imputer.pkl", "config.pkl", "lyrics_embeddings.npy"):
+        assert (tmp_path / "p2" / name).exists()
+
+
+def test_size_independent_properties_full_batch(built):
+    """BASELINE configs[1] at full size (10,000 x 3 s): properties that need no oracle."""
+    import torch
+
+    hl = built
+    B, n = 10000, 66150
+    g = torch.Generator(device="cuda").manual_seed(1)
+    y = torch.randn((B, n), device="cuda", generator=g) * 0.1
+    y[7] = 0.0
+    y[8, n // 2:] = 0.0
+    ex = hl.FeatureExtractor(ref=np.max, n_mfcc=40)
+    a = ex.extract_device(y)
+    a = {k: v.clone() for k, v in a.items()}
+    assert a["logmel"].shape == (B, 128, 130)
+    mx = a["logmel"].amax(dim=(1, 2))
+    assert torch.all(mx == 0.0), "ref=max: every clip's maximum is exactly 0 dB"
+    assert float(a["logmel"].min()) >= -80.0 and torch.all(a["logmel"][7] == 0.0)
+    assert torch.all(a["logmel"][8][:, 70:] == -80.0), "frames in the silent half sit exactly on the top_db floor"
+    assert torch.all(a["stats"][7] == 0.0) and not a["status"].any()
+    assert torch.isfinite(a["mfcc"]).all() and torch.isfinite(a["stats"]).all()
+    # deterministic, and independent of batch composition / position
+    b = ex.extract_device(y)
+    for k in ("logmel", "mfcc", "stats"):
+        assert torch.equal(a[k], b[k]), k
+    idx = torch.tensor([9999, 5, 4321, 8, 7], device="cuda")
+    c = ex.extract_device(y[idx].contiguous())
+    for k in ("logmel", "mfcc", "stats"):
+        assert torch.equal(c[k], a[k][idx]), k
+    # scaling a clip by 2: log-mel(ref=max) unchanged, MFCC[0] shifts by 10*log10(4)*sqrt(128), rms doubles
+    s = ex.extract_device((y[:64] * 2.0).contiguous())
+    assert (s["logmel"] - a["logmel"][:64]).abs().max() <= 1e-3
+    # generic kernel agrees with the register-FFT kernel on the same inputs
+    ex.force_generic(True)
+    gsub = ex.extract_device(y[:256].contiguous())
+    assert (gsub["logmel"] - a["logmel"][:256]).abs().max() <= 2e-3
+    assert (gsub["mfcc"] - a["mfcc"][:256]).abs().max() <= 1e-4 * float(a["mfcc"][:256].abs().max())
+    # and a sample of the full batch against the oracle
+    yc = y[[0, 8, 5000, 9999]].cpu().numpy()
+    for j, i in enumerate([0, 8, 5000, 9999]):
+        want = oracle_clip(yc[j], n_mfcc=40)
+        got = {k: a[k][i].cpu().numpy() for k in ("logmel", "mfcc", "stats")}
+        assert_clip(compare_clip(got, want), where=f"full batch clip {i}")

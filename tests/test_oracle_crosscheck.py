@@ -1,0 +1,57 @@
+"""Oracle vs an independent float64 direct-DFT implementation and vs torch / torchaudio; CPU only."""
+import numpy as np
+import pytest
+
+from oracle import librosa_oracle as orc
+from oracle import slow_exact as sx
+
+SR = 22050
+
+
+def _clip(seed, n=3000):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / SR
+    y = 0.3 * np.sin(2 * np.pi * 440 * t) + 0.05 * rng.standard_normal(n)
+    return y.astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["constant", "reflect", "edge"])
+def test_oracle_matches_direct_dft(mode):
+    y = _clip(1)
+    kw = dict(n_fft=512, hop_length=128)
+    ref = sx.features(y, SR, 512, 128, 40, 13, mode)
+    S = np.abs(orc.stft(y, pad_mode=mode, **kw))
+    assert np.abs(S - ref["S"]).max() <= 2e-5 * ref["S"].max()
+    mel = orc.melspectrogram(y=y, sr=SR, n_mels=40, pad_mode=mode, **kw)
+    assert np.abs(mel - ref["mel"]).max() <= 1e-5 * ref["mel"].max()
+    lm = orc.power_to_db(mel, ref=np.max)
+    assert np.abs(lm - ref["logmel"]).max() < 2e-3
+    mf = orc.mfcc(y=y, sr=SR, n_mfcc=13, n_mels=40, pad_mode=mode, **kw)
+    assert np.abs(mf - ref["mfcc"]).max() <= 1e-4 * np.abs(ref["mfcc"]).max()
+    st = ref["stats"]
+    assert np.allclose(orc.spectral_centroid(y=y, sr=SR, pad_mode=mode, **kw)[0], st[0], rtol=1e-5)
+    assert np.allclose(orc.spectral_bandwidth(y=y, sr=SR, pad_mode=mode, **kw)[0], st[1], rtol=1e-5)
+    assert np.allclose(orc.spectral_rolloff(y=y, sr=SR, pad_mode=mode, **kw)[0], st[2])
+    assert np.array_equal(orc.zero_crossing_rate(y, frame_length=512, hop_length=128)[0], st[3])
+    assert np.allclose(orc.rms(y=y, frame_length=512, hop_length=128, pad_mode=mode)[0], st[4], rtol=1e-5)
+
+
+def test_filterbank_matches_triangle_definition():
+    fb = orc.mel(sr=SR, n_fft=512, n_mels=40)
+    assert np.abs(fb - sx.mel_filterbank(SR, 512, 40)).max() < 1e-7
+
+
+def test_filterbank_matches_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    fb = orc.mel(sr=SR, n_fft=2048)
+    fb2 = ta.functional.melscale_fbanks(1025, 0.0, SR / 2, 128, SR, norm="slaney", mel_scale="slaney").numpy().T
+    assert np.abs(fb - fb2).max() < 5e-7
+
+
+def test_stft_matches_torch():
+    torch = pytest.importorskip("torch")
+    y = _clip(2, 22050)
+    D = orc.stft(y)
+    Dt = torch.stft(torch.from_numpy(y).double(), 2048, 512, window=torch.hann_window(2048, dtype=torch.float64),
+                    center=True, pad_mode="constant", return_complex=True).numpy()
+    assert np.abs(D - Dt).max() <= 1e-5 * np.abs(Dt).max()
