@@ -294,7 +294,7 @@ class FeatureExtractor:
             waves = waves[None]
         if waves.ndim != 2:
             raise ParameterError("expected (B, n) waveforms")
-        if waves.strides[1] != 4 or waves.strides[0] % 4 or waves.strides[0] < 4 * waves.shape[1]:
+        if waves.strides[1] != 4 or (waves.shape[0] > 1 and (waves.strides[0] % 4 or waves.strides[0] < 4 * waves.shape[1])):
             waves = np.ascontiguousarray(waves)
         B, n = waves.shape
         T = self.num_frames(n)
@@ -315,7 +315,8 @@ class FeatureExtractor:
         po = buf("pooled", (B, self.pooled_width(self.n_mfcc > 0))) if pooled else None
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         with self._lock:
-            _check(lib.hlmc_extract_host(self._plan, ptr(waves), B, n, waves.strides[0] // 4, ptr(lm),
+            pitch = n if B == 1 else waves.strides[0] // 4
+            _check(lib.hlmc_extract_host(self._plan, ptr(waves), B, n, pitch, ptr(lm),
                                          ptr(mf), ptr(st), ptr(sta), ptr(po), int(chunk_clips),
                                          int(n_streams)))
         del tensor_in

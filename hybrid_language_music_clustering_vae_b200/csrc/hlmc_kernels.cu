@@ -305,7 +305,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         __syncwarp();
 
         // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
-        float m0l = 0.f, m1l = 0.f, m2l = 0.f, m0h = 0.f, m1h = 0.f, m2h = 0.f;
+        float m0l = 0.f, m1l = 0.f, m0h = 0.f, m1h = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float2 w = s_tw2[i * 32 + lane];
@@ -319,8 +319,8 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
             vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
             const float d = float(i) - 7.5f;
-            m0l += sk; m1l = fmaf(d, sk, m1l); m2l = fmaf(d * d, sk, m2l);
-            m0h += sm; m1h = fmaf(-d, sm, m1h); m2h = fmaf(d * d, sm, m2h);
+            m0l += sk; m1l = fmaf(d, sk, m1l);
+            m0h += sm; m1h = fmaf(-d, sm, m1h);
         }
         // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
         const float p512 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
@@ -336,11 +336,18 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         s1 = warp_sum(s1);
         const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;   // util.normalize tiny guard
         const float cen = s1 / denom;                            // in bins
-        float q;
+        // second pass over the magnitudes held in registers: sum |X| (k - centroid)^2, the
+        // two-pass form librosa uses (one-pass moment algebra cancels badly for narrow spectra)
+        float q = 0.0f;
         {
-            const float dl = kcl - cen, dh = kch - cen;
-            q = fmaf(dl * dl, m0l, fmaf(2.0f * dl, m1l, m2l)) +
-                fmaf(dh * dh, m0h, fmaf(2.0f * dh, m1h, m2h));
+            const float cl = cen - 16.0f * lane;                 // k - c = i - cl        (low run)
+            const float ch = (1024.0f - 16.0f * lane) - cen;     // k - c = ch - i        (high run)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float dl = float(i) - cl, dh = ch - float(i);
+                q = fmaf(dl * vi[i], dl, q);
+                q = fmaf(dh * vi[16 + i], dh, q);
+            }
             if (lane == 31) { const float dm = 512.0f - cen; q = fmaf(dm * dm, s512, q); }
             q = warp_sum(q);
         }
@@ -661,7 +668,9 @@ cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, c
 // power_to_db (per-clip ref=max / top_db) fused with the DCT-II of librosa.feature.mfcc.
 // One thread per (clip, frame); DCT matrix broadcast from shared memory.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float db10(float x) { return 3.0102999566398120f * __log2f(x); }
+// 10*log10(x); __fmul_rn keeps the product from being contracted into the following
+// subtraction, so db10(max) - db10(max) is exactly 0 (librosa: ref=np.max peaks at 0.0 dB)
+__device__ __forceinline__ float db10(float x) { return __fmul_rn(3.0102999566398120f, __log2f(x)); }
 
 template <int NC>
 __global__ void __launch_bounds__(128) db_dct(const DbArgs a) {

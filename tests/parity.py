@@ -19,7 +19,8 @@ def oracle_clip(y, *, sr=22050, n_fft=2048, hop_length=512, n_mels=128, n_mfcc=4
     mel = orc.melspectrogram(y=y, sr=sr, n_mels=n_mels, power=power, **kw, **mel_kw)
     out = {"mel": mel, "logmel": orc.power_to_db(mel, ref=ref, top_db=top_db)}
     if n_mfcc:
-        out["mfcc"] = orc.mfcc(y=y, sr=sr, n_mfcc=n_mfcc, n_mels=n_mels, power=power, **kw, **mel_kw)
+        # librosa.feature.mfcc: DCT of power_to_db(melspectrogram) with ref=1.0, amin=1e-10, top_db=80
+        out["mfcc"] = orc.mfcc(S=orc.power_to_db(mel), n_mfcc=n_mfcc)
     S = np.abs(orc.stft(y, **kw))
     out["S"] = S
     stats = np.empty((5, mel.shape[-1]), np.float64)
@@ -48,6 +49,28 @@ def rolloff_margin_ok(S, sr, n_fft, got_hz, want_hz, roll_percent=0.85, margin=2
     return ok
 
 
+FP32_FLOOR = 2.0 ** -22      # per-bin magnitude floor of a float32 FFT, relative to the frame's largest bin
+
+
+def fp32_floor_allowance(S, sr, n_fft):
+    """How far centroid / bandwidth can move when every bin of the oracle's magnitude spectrum is
+    perturbed by FP32_FLOOR * max|X|.  The oracle runs librosa's float64 FFT; the device runs a
+    float32 FFT (as north_star specifies), whose rounding floor sits ~130 dB under the strongest bin.
+    For ordinary spectra the allowance is orders of magnitude below 1e-4; it only matters for
+    single-line spectra (DC, on-bin tones, n=1 clips) where bandwidth = sqrt(sum S (f-c)^2 / sum S)
+    weighs that floor by up to (sr/2)^2."""
+    S = S.astype(np.float64)
+    freq = np.arange(S.shape[0])[:, None] * (sr / n_fft)
+    tot = np.maximum(S.sum(axis=0), 1e-300)
+    a = FP32_FLOOR * S.max(axis=0)
+    cen = (freq * S).sum(axis=0) / tot
+    dev2 = (freq - cen[None, :]) ** 2
+    bw2 = (S * dev2).sum(axis=0) / tot
+    d_cen = a * np.abs(freq - cen[None, :]).sum(axis=0) / tot
+    d_bw = np.sqrt(bw2 + a * dev2.sum(axis=0) / tot) - np.sqrt(bw2)
+    return d_cen, d_bw
+
+
 def compare_clip(got: dict, want: dict, *, sr=22050, n_fft=2048, roll_percent=0.85):
     """Returns a dict of error metrics; raises nothing."""
     m = {}
@@ -65,6 +88,10 @@ def compare_clip(got: dict, want: dict, *, sr=22050, n_fft=2048, roll_percent=0.
                 okm = rolloff_margin_ok(want["S"], sr, n_fft, g[i], w[i], roll_percent)
                 m["rolloff_flips"] = int(bad.sum())
                 m["rolloff_unexplained"] = int((bad & ~okm).sum())
+            elif name in ("centroid", "bandwidth"):
+                allow = fp32_floor_allowance(want["S"], sr, n_fft)[0 if name == "centroid" else 1]
+                m[name + "_rel"] = float(np.maximum(np.abs(g[i] - w[i]) - allow, 0.0).max() / scale)
+                m[name + "_raw_rel"] = float(np.abs(g[i] - w[i]).max() / scale)
             else:
                 m[name + "_rel"] = float(np.abs(g[i] - w[i]).max() / scale)
     return m
