@@ -693,21 +693,30 @@ __global__ void __launch_bounds__(128) db_dct(const DbArgs a) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.0f;
     float* col = a.mel + (size_t)b * a.n_mels * a.T + t;
-    for (int m = 0; m < a.n_mels; ++m) {
-        const float p = col[(size_t)m * a.T];
-        const float adb = db10(fmaxf(a.amin, p));
-        col[(size_t)m * a.T] = fmaxf(adb - ref_db, floor_db);
-        if (NC > 0) {
-            float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
-            x = fmaxf(x, floor_m);
-            const float4* d4 = reinterpret_cast<const float4*>(sD + m * NC);
+    constexpr int MB = 8;                       // mel rows fetched per batch: 8 independent loads in flight
+    for (int m0 = 0; m0 < a.n_mels; m0 += MB) {
+        float pv[MB];
 #pragma unroll
-            for (int c = 0; c < NC / 4; ++c) {
-                const float4 d = d4[c];
-                acc[4 * c + 0] = fmaf(d.x, x, acc[4 * c + 0]);
-                acc[4 * c + 1] = fmaf(d.y, x, acc[4 * c + 1]);
-                acc[4 * c + 2] = fmaf(d.z, x, acc[4 * c + 2]);
-                acc[4 * c + 3] = fmaf(d.w, x, acc[4 * c + 3]);
+        for (int j = 0; j < MB; ++j) pv[j] = (m0 + j < a.n_mels) ? col[(size_t)(m0 + j) * a.T] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < MB; ++j) {
+            const int m = m0 + j;
+            if (m >= a.n_mels) break;
+            const float p = pv[j];
+            const float adb = db10(fmaxf(a.amin, p));
+            col[(size_t)m * a.T] = fmaxf(adb - ref_db, floor_db);
+            if (NC > 0) {
+                float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
+                x = fmaxf(x, floor_m);
+                const float4* d4 = reinterpret_cast<const float4*>(sD + m * NC);
+#pragma unroll
+                for (int c = 0; c < NC / 4; ++c) {
+                    const float4 d = d4[c];
+                    acc[4 * c + 0] = fmaf(d.x, x, acc[4 * c + 0]);
+                    acc[4 * c + 1] = fmaf(d.y, x, acc[4 * c + 1]);
+                    acc[4 * c + 2] = fmaf(d.z, x, acc[4 * c + 2]);
+                    acc[4 * c + 3] = fmaf(d.w, x, acc[4 * c + 3]);
+                }
             }
         }
     }
