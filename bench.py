@@ -170,7 +170,10 @@ def main():
         for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ.setdefault(k, "1")
         cores = host_cores()
-        per_step = args.cpu_sample or max(cores, min(args.clips, 8 * cores))
+        # bounded sample: a pilot sizes each step to ~12 s / steps of CPU work on this box
+        pilot = synth.synth_batch(4 * cores, n, seed=20261, mixture=False)
+        rate = len(pilot) / cpu_reference_run(pilot, cores)
+        per_step = args.cpu_sample or int(max(cores, min(args.clips, rate * 12.0 / max(args.steps, 1))))
         clips = synth.synth_batch(per_step, n, seed=20261, mixture=False)
         for _ in range(max(1, min(args.warmup, 1))):
             cpu_reference_run(clips[: max(cores, per_step // 4)], cores)
@@ -336,7 +339,9 @@ def main():
         for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ.setdefault(k, "1")
         cores = host_cores()
-        ns = args.cpu_sample or max(cores, min(B, 16 * cores))
+        pilot_n = min(B, 4 * cores)
+        rate = pilot_n / cpu_reference_run(h_wave_t.numpy()[:pilot_n], cores)
+        ns = args.cpu_sample or int(max(cores, min(B, rate * 12.0)))      # ~12 s of CPU work
         t = cpu_reference_run(h_wave_t.numpy()[:ns], cores)
         cpu = {"value": ns / t, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {ns} clips of the same batch, oracle port of the reference's "
