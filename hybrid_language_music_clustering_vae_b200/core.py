@@ -269,10 +269,13 @@ class FeatureExtractor:
 
     # -- host path (the reference-facing call) ---------------------------------
     def extract_host(self, waves, *, logmel=True, mfcc=True, stats=True, status=True, pooled=False,
-                     chunk_clips=0, n_streams=3, out=None):
-        """(B, n) host float32 (numpy or CPU torch, ideally pinned) -> dict of numpy arrays.
+                     chunk_clips=0, n_streams=3, out=None, pad_to=None):
+        """(B, n) host float32 -- or int16 PCM -- (numpy or CPU torch, ideally pinned) -> dict of numpy arrays.
 
-        H2D copies, kernels and D2H copies are overlapped inside the C library.
+        H2D copies, kernels and D2H copies are overlapped inside the C library.  int16 input is
+        converted on the device as librosa.load does for PCM16 files (x / 32768); ``pad_to`` right
+        zero-pads every clip on the device to that many samples, the scripts' ``np.pad`` to
+        ``sample_rate * duration`` ([R] src/1_preprocessing.py:146-148).
         """
         tensor_in = None
         try:
@@ -286,18 +289,24 @@ class FeatureExtractor:
         except ImportError:  # pragma: no cover
             pass
         waves = np.asarray(waves)
-        if not np.issubdtype(waves.dtype, np.floating):
-            raise ParameterError("Audio data must be floating-point")
-        if waves.dtype != np.float32:
-            waves = waves.astype(np.float32)
+        pcm16 = waves.dtype == np.int16
+        if not pcm16:
+            if not np.issubdtype(waves.dtype, np.floating):
+                raise ParameterError("Audio data must be floating-point")
+            if waves.dtype != np.float32:
+                waves = waves.astype(np.float32)
+        esz = waves.dtype.itemsize
         if waves.ndim == 1:
             waves = waves[None]
         if waves.ndim != 2:
             raise ParameterError("expected (B, n) waveforms")
-        if waves.strides[1] != 4 or (waves.shape[0] > 1 and (waves.strides[0] % 4 or waves.strides[0] < 4 * waves.shape[1])):
+        if waves.strides[1] != esz or (waves.shape[0] > 1 and (waves.strides[0] % esz or waves.strides[0] < esz * waves.shape[1])):
             waves = np.ascontiguousarray(waves)
         B, n = waves.shape
-        T = self.num_frames(n)
+        n_total = int(pad_to) if pad_to else n
+        if n_total < n:
+            raise ParameterError("pad_to is shorter than the clips")
+        T = self.num_frames(n_total)
         mfcc = bool(mfcc) and self.n_mfcc > 0
         out = dict(out) if out else {}
 
@@ -315,10 +324,10 @@ class FeatureExtractor:
         po = buf("pooled", (B, self.pooled_width(self.n_mfcc > 0))) if pooled else None
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         with self._lock:
-            pitch = n if B == 1 else waves.strides[0] // 4
-            _check(lib.hlmc_extract_host(self._plan, ptr(waves), B, n, pitch, ptr(lm),
-                                         ptr(mf), ptr(st), ptr(sta), ptr(po), int(chunk_clips),
-                                         int(n_streams)))
+            pitch = n if B == 1 else waves.strides[0] // esz
+            _check(lib.hlmc_extract_host_ex(self._plan, ptr(waves), 1 if pcm16 else 0, B, n, pitch, n_total,
+                                            ptr(lm), ptr(mf), ptr(st), ptr(sta), ptr(po), int(chunk_clips),
+                                            int(n_streams)))
         del tensor_in
         return out
 

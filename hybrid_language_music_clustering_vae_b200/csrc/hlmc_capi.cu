@@ -35,6 +35,7 @@ struct HostPipeSlot {
     float* d_wave = nullptr; float* d_logmel = nullptr; float* d_mfcc = nullptr;
     float* d_stats = nullptr; float* d_pooled = nullptr; float* d_clipmax = nullptr;
     int32_t* d_status = nullptr;
+    int16_t* d_raw = nullptr; size_t raw_elems = 0;     // PCM16 staging (hlmc_extract_host_ex)
 };
 
 struct hlmc_plan {
@@ -160,7 +161,7 @@ void hlmc_plan_destroy(hlmc_plan* plan) {
     for (auto& s : plan->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(plan->d_fast); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
@@ -542,7 +543,7 @@ static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, 
     for (auto& s : pl->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     pl->slots.assign(n_streams, HostPipeSlot());
@@ -562,11 +563,18 @@ static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, 
     return HLMC_OK;
 }
 
-int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n, int64_t h_pitch,
-                      float* h_logmel, float* h_mfcc, float* h_stats, int32_t* h_status, float* h_pooled,
-                      int64_t chunk_clips, int n_streams) {
+int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format, int64_t B,
+                         int64_t n_valid, int64_t h_pitch, int64_t n_total, float* h_logmel, float* h_mfcc,
+                         float* h_stats, int32_t* h_status, float* h_pooled, int64_t chunk_clips,
+                         int n_streams) {
+    if (sample_format != HLMC_SAMPLES_F32 && sample_format != HLMC_SAMPLES_PCM16)
+        return fail(HLMC_ERR_PARAM, "unknown sample_format");
+    if (n_total < n_valid) return fail(HLMC_ERR_PARAM, "n_total < n_valid");
     int64_t T;
-    int rc = check_batch(plan, h_wave, B, n, h_pitch, &T);
+    const int64_t n = n_total;
+    if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
+    if (h_pitch < n_valid) return fail(HLMC_ERR_PARAM, "pitch < n");
+    int rc = check_batch(plan, h_wave, B, n, n, &T);
     if (rc != HLMC_OK) return rc;
     plan->last_h2d = plan->last_d2h = 0;
     if (B == 0) return HLMC_OK;
@@ -582,6 +590,19 @@ int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n
     rc = ensure_slots(plan, n_streams, chunk_clips, n, T, 0);
     if (rc != HLMC_OK) return rc;
     const int64_t dp = (n + 3) & ~int64_t(3);
+    const int64_t rp = (n_valid + 7) & ~int64_t(7);           // PCM16 staging pitch (16-B rows)
+    const bool pcm = (sample_format == HLMC_SAMPLES_PCM16);
+    const size_t esz = pcm ? 2 : 4;
+    if (pcm) {
+        for (auto& s : plan->slots) {
+            if (s.raw_elems < (size_t)(plan->slot_chunk * rp)) {
+                cudaFree(s.d_raw);
+                s.d_raw = nullptr;
+                CK(cudaMalloc((void**)&s.d_raw, (size_t)plan->slot_chunk * rp * 2));
+                s.raw_elems = (size_t)plan->slot_chunk * rp;
+            }
+        }
+    }
     const int nm = plan->p.n_mels, nc = plan->p.n_mfcc;
     const bool want_mfcc = (h_mfcc != nullptr) || (h_pooled != nullptr && nc > 0);
     const int pooled_w = 2 * nm + 2 * (want_mfcc ? nc : 0) + 10;
@@ -589,9 +610,20 @@ int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n
     for (int64_t i = 0; done < B; ++i) {
         HostPipeSlot& s = plan->slots[i % n_streams];
         const int64_t c = (B - done < chunk_clips) ? (B - done) : chunk_clips;
-        CK(cudaMemcpy2DAsync(s.d_wave, (size_t)dp * 4, h_wave + done * h_pitch, (size_t)h_pitch * 4,
-                             (size_t)n * 4, (size_t)c, cudaMemcpyHostToDevice, s.stream));
-        plan->last_h2d += c * n * 4;
+        const char* src = static_cast<const char*>(h_wave) + (size_t)done * h_pitch * esz;
+        if (pcm) {
+            // [R] librosa.load on a PCM16 file: float32 = int16 / 32768; then the scripts' zero pad
+            CK(cudaMemcpy2DAsync(s.d_raw, (size_t)rp * 2, src, (size_t)h_pitch * 2, (size_t)n_valid * 2,
+                                 (size_t)c, cudaMemcpyHostToDevice, s.stream));
+            CK(launch_pcm16_to_f32(s.d_raw, rp, s.d_wave, dp, c, n_valid, n, s.stream));
+        } else {
+            CK(cudaMemcpy2DAsync(s.d_wave, (size_t)dp * 4, src, (size_t)h_pitch * 4, (size_t)n_valid * 4,
+                                 (size_t)c, cudaMemcpyHostToDevice, s.stream));
+            if (n > n_valid)   // [R] np.pad(audio, (0, expected - len(audio))) done on the device
+                CK(cudaMemset2DAsync(s.d_wave + n_valid, (size_t)dp * 4, 0, (size_t)(n - n_valid) * 4,
+                                     (size_t)c, s.stream));
+        }
+        plan->last_h2d += c * n_valid * (int64_t)esz;
         rc = hlmc_extract_device(plan, s.d_wave, c, n, dp, s.d_logmel, want_mfcc ? s.d_mfcc : nullptr,
                                  s.d_stats, s.d_status, s.d_clipmax, s.stream);
         if (rc != HLMC_OK) return rc;
@@ -625,6 +657,13 @@ int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n
     }
     for (auto& s : plan->slots) CK(cudaStreamSynchronize(s.stream));
     return HLMC_OK;
+}
+
+int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n, int64_t h_pitch,
+                      float* h_logmel, float* h_mfcc, float* h_stats, int32_t* h_status, float* h_pooled,
+                      int64_t chunk_clips, int n_streams) {
+    return hlmc_extract_host_ex(plan, h_wave, HLMC_SAMPLES_F32, B, n, h_pitch, n, h_logmel, h_mfcc, h_stats,
+                                h_status, h_pooled, chunk_clips, n_streams);
 }
 
 void hlmc_last_transfer_bytes(const hlmc_plan* plan, int64_t* h2d, int64_t* d2h) {

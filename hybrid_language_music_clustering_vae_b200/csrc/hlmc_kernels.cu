@@ -894,6 +894,32 @@ cudaError_t launch_fix_frames(const float* in, float* out, long long B, int rows
 }
 
 // ---------------------------------------------------------------------------
+// Front end of [R] load_audio_file for PCM16 sources: float32 = int16 / 32768 (what
+// librosa.load -> soundfile returns) and the scripts' right zero-pad to `n_total` samples,
+// done on the device so only the valid int16 samples cross PCIe.
+// ---------------------------------------------------------------------------
+__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ raw, long long raw_pitch,
+                                    float* __restrict__ out, long long pitch, long long n_valid,
+                                    long long n_total) {
+    const long long b = blockIdx.y;
+    const int16_t* src = raw + b * raw_pitch;
+    float* dst = out + b * pitch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (i < n_valid) ? float(src[i]) * (1.0f / 32768.0f) : 0.0f;
+}
+cudaError_t launch_pcm16_to_f32(const int16_t* raw, long long raw_pitch, float* out, long long pitch,
+                                long long B, long long n_valid, long long n_total, cudaStream_t stream) {
+    if (B <= 0 || n_total <= 0) return cudaSuccess;
+    int gx = (int)((n_total + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 128) gx = 128;
+    pcm16_to_f32_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(raw, raw_pitch, out, pitch, n_valid, n_total);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // FP32 roofline denominator: independent FMA chains, every SM sub-partition busy.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float seed) {

@@ -183,6 +183,20 @@ int hlmc_extract_host(hlmc_plan *plan, const float *h_wave, int64_t B, int64_t n
                       int64_t h_pitch, float *h_logmel, float *h_mfcc, float *h_stats,
                       int32_t *h_status, float *h_pooled, int64_t chunk_clips, int n_streams);
 
+/* Same with the front end of the scripts' load_audio_file ([R] src/1_preprocessing.py:137-153,
+ * src/1_preprocessing_advanced.py:79-94) folded in:
+ *   sample_format HLMC_SAMPLES_PCM16: h_wave holds int16 PCM as stored in the WAV file; the device
+ *     converts with float32 = int16 / 32768 (what librosa.load returns for PCM16), so only 2 bytes
+ *     per sample cross PCIe;
+ *   n_total > n_valid: every clip is right zero-padded on the device to n_total samples (the
+ *     scripts' np.pad to sample_rate * duration) instead of shipping the zeros.
+ * h_pitch is in elements of the given format.  Frame counts follow n_total.                  */
+enum { HLMC_SAMPLES_F32 = 0, HLMC_SAMPLES_PCM16 = 1 };
+int hlmc_extract_host_ex(hlmc_plan *plan, const void *h_wave, int sample_format, int64_t B,
+                         int64_t n_valid, int64_t h_pitch, int64_t n_total, float *h_logmel,
+                         float *h_mfcc, float *h_stats, int32_t *h_status, float *h_pooled,
+                         int64_t chunk_clips, int n_streams);
+
 /* Bytes moved by the last hlmc_extract_host call on this plan.               */
 void hlmc_last_transfer_bytes(const hlmc_plan *plan, int64_t *h2d, int64_t *d2h);
 

@@ -332,3 +332,26 @@ def test_size_independent_properties_full_batch(built):
         want = oracle_clip(yc[j], n_mfcc=40)
         got = {k: a[k][i].cpu().numpy() for k in ("logmel", "mfcc", "stats")}
         assert_clip(compare_clip(got, want), where=f"full batch clip {i}")
+
+
+def test_pcm16_and_device_pad_front_end(built):
+    """[R] load_audio_file: librosa.load of a PCM16 file (int16 / 32768) + np.pad to the target length,
+    with the conversion and the padding done on the device."""
+    hl = built
+    rng = np.random.default_rng(77)
+    y16 = rng.integers(-20000, 20000, size=(7, 22050)).astype(np.int16)
+    yf = (y16.astype(np.float32) / np.float32(32768.0))
+    padded = np.zeros((7, 66150), np.float32)
+    padded[:, :22050] = yf
+    ex = hl.FeatureExtractor(ref=np.max, n_mfcc=40)
+    ref = ex.extract_host(padded)
+    a = ex.extract_host(y16, pad_to=66150, chunk_clips=3)
+    assert ex.last_transfer_bytes()[0] == y16.nbytes
+    b = ex.extract_host(yf, pad_to=66150)
+    assert ex.last_transfer_bytes()[0] == yf.nbytes
+    for k in ("logmel", "mfcc", "stats", "status"):
+        assert np.array_equal(a[k], ref[k]) and np.array_equal(b[k], ref[k]), k
+    want = oracle_clip(padded[2], n_mfcc=40)
+    assert_clip(compare_clip({k: a[k][2] for k in ("logmel", "mfcc", "stats")}, want), where="pcm16 clip 2")
+    with pytest.raises(hl.ParameterError):
+        ex.extract_host(y16, pad_to=100)
