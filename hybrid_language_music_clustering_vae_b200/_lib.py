@@ -20,6 +20,7 @@ EXPORTS = (
     "hlmc_power_to_db_device", "hlmc_pool_device", "hlmc_fix_frames_device",
     "hlmc_extract_host", "hlmc_last_transfer_bytes", "hlmc_measure_fp32_peak",
     "hlmc_plan_set_timing", "hlmc_plan_read_timing", "hlmc_extract_host_ex",
+    "hlmc_chroma_workspace_bytes", "hlmc_extract_device_ex", "hlmc_pool_device_ex",
 )
 
 HLMC_OK, HLMC_ERR_PARAM, HLMC_ERR_UNSUPPORTED, HLMC_ERR_CUDA, HLMC_ERR_NOMEM = 0, -1, -2, -3, -4
@@ -72,6 +73,10 @@ def _load():
     lib.hlmc_fix_frames_device.argtypes = [vp, vp, i64, i64, i64, i64, C.c_int, vp]
     lib.hlmc_extract_host.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, C.c_int]
     lib.hlmc_extract_host_ex.argtypes = [vp, vp, C.c_int, i64, i64, i64, i64, vp, vp, vp, vp, vp, i64, C.c_int]
+    lib.hlmc_chroma_workspace_bytes.argtypes = [vp, i64, i64]
+    lib.hlmc_chroma_workspace_bytes.restype = i64
+    lib.hlmc_extract_device_ex.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.hlmc_pool_device_ex.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp]
     lib.hlmc_last_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.hlmc_last_transfer_bytes.restype = None
     lib.hlmc_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

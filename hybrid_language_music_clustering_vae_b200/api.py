@@ -166,6 +166,28 @@ class _Feature:
         return m.reshape(lead + tuple(m.shape[1:]))
 
     @staticmethod
+    def chroma_stft(*, y=None, sr=22050, S=None, norm=np.inf, n_fft=2048, hop_length=512, win_length=None,
+                    window="hann", center=True, pad_mode="constant", tuning=None, n_chroma=12, **kwargs):
+        """librosa.feature.chroma_stft -> (..., 12, T) float32, tuning estimated per clip."""
+        import torch
+
+        if S is not None or tuning is not None or n_chroma != 12 or norm != np.inf or kwargs:
+            raise UnsupportedError("chroma_stft: only y input with the default tuning=None, n_chroma=12, "
+                                   "norm=inf and filterbank parameters is implemented on device")
+        yb, lead, on_dev = _prep(y)
+        ex = get_extractor(sr=sr, **_stft_kw(n_fft, hop_length, win_length, window, center, pad_mode), n_mfcc=0,
+                           device=_device_of(yb, on_dev))
+        if on_dev:
+            c = ex.extract_device(yb, mfcc=False, stats=False, chroma=True)["chroma"]
+            return c.reshape(lead + tuple(c.shape[1:]))
+        if not np.isfinite(yb).all():
+            raise ParameterError("Audio buffer is not finite everywhere")
+        dev = torch.device("cuda", ex.device)
+        c = ex.extract_device(torch.from_numpy(np.ascontiguousarray(yb, dtype=np.float32)).to(dev), mfcc=False,
+                              stats=False, chroma=True)["chroma"].cpu().numpy()
+        return c.reshape(lead + c.shape[1:])
+
+    @staticmethod
     def _stat(idx, y, kw, dtype64=True):
         res, lead = _Feature._run(y, dict(n_mfcc=0, **kw), want="stats")
         s = res["stats"][:, idx:idx + 1, :]

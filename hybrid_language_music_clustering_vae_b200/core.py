@@ -64,6 +64,11 @@ def _ref_to_mode(ref):
     return _lib.REF_VALUE, float(abs(ref))
 
 
+def _row_pitch(w):
+    """Row pitch in elements; a single-row tensor may carry an arbitrary stride(0)."""
+    return w.shape[1] if w.shape[0] == 1 else w.stride(0)
+
+
 class FeatureExtractor:
     """Fused log-mel + MFCC + spectral statistics for batches of equal-length clips."""
 
@@ -168,8 +173,8 @@ class FeatureExtractor:
         _check(lib.hlmc_plan_dct_basis(self._plan, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def pooled_width(self, with_mfcc=True) -> int:
-        return 2 * self.n_mels + (2 * self.n_mfcc if with_mfcc else 0) + 10
+    def pooled_width(self, with_mfcc=True, with_chroma=False) -> int:
+        return 2 * self.n_mels + (2 * self.n_mfcc if with_mfcc else 0) + 10 + (24 if with_chroma else 0)
 
     # -- device-resident path -----------------------------------------------
     def _as_cuda_batch(self, waves):
@@ -189,12 +194,15 @@ class FeatureExtractor:
             raise ParameterError(f"tensor is on cuda:{waves.device.index}, plan on cuda:{self.device}")
         return waves
 
-    def extract_device(self, waves, *, mfcc=True, stats=True, status=True, pooled=False, out=None):
+    def extract_device(self, waves, *, mfcc=True, stats=True, status=True, pooled=False, chroma=False,
+                       out=None):
         """(B, n) CUDA float32 -> dict of CUDA tensors; asynchronous on the current stream.
 
         Keys: ``logmel`` (B, n_mels, T), ``mfcc`` (B, n_mfcc, T), ``stats`` (B, 5, T),
-        ``status`` (B,) int32, ``pooled`` (B, 2*n_mels + 2*n_mfcc + 10).  ``out`` may hold
-        preallocated tensors under the same keys (plus ``clipmax``).
+        ``status`` (B,) int32, ``pooled`` (B, 2*n_mels + 2*n_mfcc + 10 [+ 24 with chroma]);
+        with ``chroma=True`` also ``chroma`` (B, 12, T) = librosa.feature.chroma_stft and
+        ``tuning`` (B,) = librosa.estimate_tuning per clip.  ``out`` may hold preallocated
+        tensors under the same keys (plus ``clipmax``).
         """
         import torch
 
@@ -219,12 +227,22 @@ class FeatureExtractor:
         cm = buf("clipmax", (B,))
         stream = torch.cuda.current_stream(dev).cuda_stream
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        _check(lib.hlmc_extract_device(self._plan, ptr(waves), B, n, waves.stride(0), ptr(logmel), ptr(mf),
-                                       ptr(st), ptr(sta), ptr(cm), C.c_void_p(stream)))
+        ch = tu = work = None
+        wbytes = 0
+        if chroma:
+            wbytes = int(lib.hlmc_chroma_workspace_bytes(self._plan, B, n))
+            if wbytes < 0:
+                _check(wbytes)
+            ch = buf("chroma", (B, 12, T))
+            tu = buf("tuning", (B,))
+            work = buf("chroma_work", (wbytes,), torch.uint8)
+        _check(lib.hlmc_extract_device_ex(self._plan, ptr(waves), B, n, _row_pitch(waves), ptr(logmel), ptr(mf),
+                                          ptr(st), ptr(sta), ptr(cm), ptr(ch), ptr(tu), ptr(work), wbytes,
+                                          C.c_void_p(stream)))
         if pooled:
-            po = buf("pooled", (B, self.pooled_width(mfcc)))
-            _check(lib.hlmc_pool_device(self._plan, ptr(logmel), ptr(mf), ptr(st), B, T, ptr(po),
-                                        C.c_void_p(stream)))
+            po = buf("pooled", (B, self.pooled_width(mfcc, bool(chroma))))
+            _check(lib.hlmc_pool_device_ex(self._plan, ptr(logmel), ptr(mf), ptr(st), ptr(ch), B, T, ptr(po),
+                                           C.c_void_p(stream)))
         return out
 
     def melspectrogram_device(self, waves, *, stats=False):
@@ -237,7 +255,7 @@ class FeatureExtractor:
         st = torch.empty((B, 5, T), dtype=torch.float32, device=waves.device) if stats else None
         stream = torch.cuda.current_stream(waves.device).cuda_stream
         _check(lib.hlmc_melspectrogram_device(
-            self._plan, C.c_void_p(waves.data_ptr()), B, n, waves.stride(0), C.c_void_p(mel.data_ptr()),
+            self._plan, C.c_void_p(waves.data_ptr()), B, n, _row_pitch(waves), C.c_void_p(mel.data_ptr()),
             C.c_void_p(st.data_ptr()) if st is not None else None, None, C.c_void_p(stream)))
         return (mel, st) if stats else mel
 
@@ -251,7 +269,7 @@ class FeatureExtractor:
         st = torch.empty((B, 5, T), dtype=torch.float32, device=waves.device)
         stream = torch.cuda.current_stream(waves.device).cuda_stream
         _check(lib.hlmc_melspectrogram_device(
-            self._plan, C.c_void_p(waves.data_ptr()), B, n, waves.stride(0), None,
+            self._plan, C.c_void_p(waves.data_ptr()), B, n, _row_pitch(waves), None,
             C.c_void_p(st.data_ptr()), None, C.c_void_p(stream)))
         return st
 
@@ -263,7 +281,7 @@ class FeatureExtractor:
         T = self.num_frames(n)
         spec = torch.empty((B, self.n_bins, T, 2), dtype=torch.float32, device=waves.device)
         stream = torch.cuda.current_stream(waves.device).cuda_stream
-        _check(lib.hlmc_stft_device(self._plan, C.c_void_p(waves.data_ptr()), B, n, waves.stride(0),
+        _check(lib.hlmc_stft_device(self._plan, C.c_void_p(waves.data_ptr()), B, n, _row_pitch(waves),
                                     C.c_void_p(spec.data_ptr()), C.c_void_p(stream)))
         return torch.view_as_complex(spec)
 

@@ -54,6 +54,9 @@ struct hlmc_plan {
     std::vector<HostPipeSlot> slots;
     int64_t slot_chunk = 0, slot_n = 0; int slot_flags = 0;
     int64_t last_h2d = 0, last_d2h = 0;
+    // chroma_stft (built lazily): 100 filterbanks (one per tuning bin) + histogram edges
+    float* d_chroma_fb = nullptr; double* d_edges = nullptr;
+    int pip_klo = 0, pip_khi = 0, cand_per_frame = 0;
     // optional per-kernel timing (events recorded on the launching stream)
     int timing = 0;
     std::vector<cudaEvent_t> ev;      // triples: before frames, after frames, after db_dct
@@ -130,6 +133,75 @@ static cudaError_t upload(T** dptr, const std::vector<T>& h) {
     return e;
 }
 
+// librosa.filters.chroma(sr, n_fft, tuning, n_chroma=12, ctroct=5, octwidth=2, norm=2, base_c=True)
+// restated in float64; returns (12, 1 + n_fft/2) float32, row 0 = C.
+static void build_chroma_fb(int sr, int n_fft, double tuning, std::vector<float>& out) {
+    const int nc = 12, F = n_fft / 2 + 1;
+    std::vector<double> frq(n_fft), bw(n_fft);
+    const double a440 = 440.0 * pow(2.0, tuning / nc);
+    const double step = double(sr) / double(n_fft);
+    for (int i = 1; i < n_fft; ++i) frq[i] = nc * log2((i * step) / (a440 / 16.0));
+    frq[0] = frq[1] - 1.5 * nc;
+    for (int i = 0; i + 1 < n_fft; ++i) bw[i] = std::max(frq[i + 1] - frq[i], 1.0);
+    bw[n_fft - 1] = 1.0;
+    std::vector<double> w((size_t)nc * F);
+    for (int i = 0; i < F; ++i) {
+        double col[12], nrm = 0.0;
+        for (int c = 0; c < nc; ++c) {
+            double D = fmod(frq[i] - c + 6.0 + 10.0 * nc, double(nc)) - 6.0;
+            const double z = 2.0 * D / bw[i];
+            col[c] = exp(-0.5 * z * z);
+            nrm += col[c] * col[c];
+        }
+        nrm = sqrt(nrm);
+        if (nrm < 2.2250738585072014e-308) nrm = 1.0;
+        const double o = (frq[i] / nc - 5.0) / 2.0;
+        const double oct = exp(-0.5 * o * o);
+        for (int c = 0; c < nc; ++c) w[(size_t)c * F + i] = col[c] / nrm * oct;
+    }
+    out.resize((size_t)nc * F);
+    for (int c = 0; c < nc; ++c)                      // np.roll(wts, -3, axis=0)
+        for (int i = 0; i < F; ++i) out[(size_t)c * F + i] = float(w[(size_t)((c + 3) % nc) * F + i]);
+}
+
+static int ensure_chroma_tables(hlmc_plan* pl) {
+    if (pl->d_chroma_fb) return HLMC_OK;
+    if (pl->p.n_fft != kFastNfft || !pl->fast_ok)
+        return fail(HLMC_ERR_UNSUPPORTED, "chroma_stft on device needs n_fft = 2048 (the register-FFT kernel)");
+    if (pl->p.power != 2.0f) return fail(HLMC_ERR_UNSUPPORTED, "chroma_stft on device needs a power=2 plan");
+    const int F = pl->F;
+    // bins np.linspace(-0.5, 0.5, 101) of librosa.pitch_tuning (resolution 0.01)
+    std::vector<double> edges(kTuningBins + 1);
+    const double step = (0.5 - (-0.5)) / double(kTuningBins);
+    for (int i = 0; i <= kTuningBins; ++i) edges[i] = (i == kTuningBins) ? 0.5 : i * step + (-0.5);
+    std::vector<float> all((size_t)kTuningBins * kChromaFbFloats, 0.0f), fb;
+    for (int tb = 0; tb < kTuningBins; ++tb) {
+        build_chroma_fb(pl->p.sr, pl->p.n_fft, edges[tb], fb);
+        float* dst = &all[(size_t)tb * kChromaFbFloats];
+        for (int c = 0; c < kChroma; ++c) {
+            for (int l = 0; l < 32; ++l)
+                for (int j = 0; j < 32; ++j) {
+                    const int k = (j < 16) ? 16 * l + j : 1024 - 16 * l - (j - 16);
+                    dst[(((size_t)c * 8 + j / 4) * 32 + l) * 4 + (j % 4)] = fb[(size_t)c * F + k];
+                }
+            dst[kChroma * 32 * 32 + c] = fb[(size_t)c * F + 512];
+        }
+    }
+    // piptrack's frequency mask: fmin=150 <= f < fmax=4000 (librosa.estimate_tuning defaults)
+    const double val = 1.0 / (double(pl->p.n_fft) * (1.0 / double(pl->p.sr)));
+    const double fmax = std::min(4000.0, double(pl->p.sr) / 2.0);
+    int klo = 1, khi = 1;
+    while (klo < F - 1 && klo * val < 150.0) ++klo;
+    khi = klo;
+    while (khi < F - 1 && khi * val < fmax) ++khi;
+    pl->pip_klo = klo; pl->pip_khi = khi;
+    pl->cand_per_frame = (khi - klo + 1) / 2 + 1;
+    cudaError_t e;
+    if ((e = upload(&pl->d_chroma_fb, all)) != cudaSuccess) return cuda_fail(e, "upload chroma filterbanks");
+    if ((e = upload(&pl->d_edges, edges)) != cudaSuccess) return cuda_fail(e, "upload tuning edges");
+    return HLMC_OK;
+}
+
 extern "C" {
 
 int hlmc_abi_version(void) { return HLMC_ABI_VERSION; }
@@ -166,7 +238,7 @@ void hlmc_plan_destroy(hlmc_plan* plan) {
     }
     cudaFree(plan->d_fast); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
     cudaFree(plan->d_mel_lo); cudaFree(plan->d_mel_len); cudaFree(plan->d_mel_off); cudaFree(plan->d_mel_w);
-    cudaFree(plan->d_dct_t);
+    cudaFree(plan->d_dct_t); cudaFree(plan->d_chroma_fb); cudaFree(plan->d_edges);
     delete plan;
 }
 
@@ -383,22 +455,30 @@ int hlmc_plan_dct_basis(const hlmc_plan* plan, float* h_out) {
     return HLMC_OK;
 }
 
-static int run_frames(hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, int64_t pitch, int T,
-                      float* d_mel, float* d_stats, int32_t* d_status, float* d_clipmax, float* d_spec,
-                      cudaStream_t st) {
+static FrameArgs make_frame_args(const hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, int64_t pitch, int T) {
     FrameArgs a{};
     a.wave = d_wave; a.pitch = pitch; a.B = (int)B; a.n = (int)n; a.T = T;
     a.n_fft = pl->p.n_fft; a.hop = pl->p.hop_length; a.pad = pl->p.center ? pl->p.n_fft / 2 : 0;
     a.pad_mode = pl->p.pad_mode; a.n_mels = pl->p.n_mels; a.use_mag = (pl->p.power == 1.0f) ? 1 : 0;
     a.binhz = float(double(pl->p.sr) / double(pl->p.n_fft));
     a.roll_percent = pl->p.roll_percent; a.zcr_thr = pl->p.zcr_threshold;
+    a.pip_klo = pl->pip_klo; a.pip_khi = pl->pip_khi; a.pip_threshold = 0.1f;
+    return a;
+}
+
+static int run_frames(hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, int64_t pitch, int T,
+                      float* d_mel, float* d_stats, int32_t* d_status, float* d_clipmax, float* d_spec,
+                      cudaStream_t st, float2* cand = nullptr, int* cand_count = nullptr, int cand_cap = 0) {
+    FrameArgs a = make_frame_args(pl, d_wave, B, n, pitch, T);
     a.mel_out = d_mel; a.stats = d_stats; a.status = d_status;
     a.clipmax = reinterpret_cast<unsigned int*>(d_clipmax); a.spec = d_spec;
+    a.cand = cand; a.cand_count = cand_count; a.cand_cap = cand_cap;
     if (d_clipmax) CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));
     if (d_status) CK(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
     if (pl->fast_ok && !pl->force_generic && d_spec == nullptr) {
         CK(launch_frames_fast(a, pl->d_fast, pl->ft, pl->num_sms, st));
     } else {
+        if (cand) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs the register-FFT kernel");
         GenericTables gt{pl->d_win, pl->d_twm, pl->d_tws, pl->d_mel_lo, pl->d_mel_len, pl->d_mel_off, pl->d_mel_w};
         CK(launch_frames_generic(a, gt, st));
     }
@@ -417,9 +497,21 @@ static int check_batch(const hlmc_plan* pl, const void* wave, int64_t B, int64_t
     return HLMC_OK;
 }
 
-int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
-                        float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
-                        float* d_clipmax, void* stream) {
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int64_t hlmc_chroma_workspace_bytes(hlmc_plan* plan, int64_t B, int64_t n) {
+    if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
+    int rc = ensure_chroma_tables(plan);
+    if (rc != HLMC_OK) return rc;
+    const int64_t T = hlmc_num_frames(&plan->p, n);
+    if (T < 0) return T;
+    return (int64_t)(2 * align256((size_t)B * 4) + (size_t)B * T * plan->cand_per_frame * sizeof(float2));
+}
+
+int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                           float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
+                           float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
+                           int64_t work_bytes, void* stream) {
     int64_t T;
     int rc = check_batch(plan, d_wave, B, n, pitch, &T);
     if (rc != HLMC_OK) return rc;
@@ -428,13 +520,29 @@ int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t
     if (d_mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
     CK(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // chroma: piptrack candidates come out of the same pass as the other features
+    float2* cand = nullptr; int* cand_count = nullptr; int* tuning_idx = nullptr; int cand_cap = 0;
+    if (d_chroma) {
+        rc = ensure_chroma_tables(plan);
+        if (rc != HLMC_OK) return rc;
+        if (plan->force_generic) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs the register-FFT kernel");
+        const int64_t need = hlmc_chroma_workspace_bytes(plan, B, n);
+        if (!d_work || work_bytes < need) return fail(HLMC_ERR_PARAM, "chroma workspace too small");
+        char* wsp = static_cast<char*>(d_work);
+        cand_count = reinterpret_cast<int*>(wsp);
+        tuning_idx = reinterpret_cast<int*>(wsp + align256((size_t)B * 4));
+        cand = reinterpret_cast<float2*>(wsp + 2 * align256((size_t)B * 4));
+        cand_cap = (int)(T * plan->cand_per_frame);
+        CK(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
+    }
     cudaEvent_t ev3[3] = {nullptr, nullptr, nullptr};
     if (plan->timing) {
         for (auto& e : ev3) CK(cudaEventCreate(&e));
         CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));   // keep the memsets out of the bracket
     }
     if (plan->timing) CK(cudaEventRecord(ev3[0], st));
-    rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_logmel, d_stats, d_status, d_clipmax, nullptr, st);
+    rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_logmel, d_stats, d_status, d_clipmax, nullptr, st,
+                    cand, cand_count, cand_cap);
     if (rc != HLMC_OK) return rc;
     if (plan->timing) CK(cudaEventRecord(ev3[1], st));
     DbArgs d{};
@@ -447,7 +555,20 @@ int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t
         CK(cudaEventRecord(ev3[2], st));
         for (auto& e : ev3) plan->ev.push_back(e);
     }
+    if (d_chroma) {
+        CK(launch_tuning(cand, cand_count, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
+        FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
+        ChromaArgs ca{tuning_idx, plan->d_chroma_fb, d_chroma};
+        CK(launch_chroma_fast(a, ca, plan->d_fast, plan->ft, plan->num_sms, st));
+    }
     return HLMC_OK;
+}
+
+int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                        float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
+                        float* d_clipmax, void* stream) {
+    return hlmc_extract_device_ex(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax,
+                                  nullptr, nullptr, nullptr, 0, stream);
 }
 
 int hlmc_plan_set_timing(hlmc_plan* plan, int enable) {
@@ -514,14 +635,19 @@ int hlmc_power_to_db_device(const float* d_in, float* d_out, int64_t B, int64_t 
     return HLMC_OK;
 }
 
-int hlmc_pool_device(hlmc_plan* plan, const float* d_logmel, const float* d_mfcc, const float* d_stats,
-                     int64_t B, int64_t T, float* d_pooled, void* stream) {
+int hlmc_pool_device_ex(hlmc_plan* plan, const float* d_logmel, const float* d_mfcc, const float* d_stats,
+                        const float* d_chroma, int64_t B, int64_t T, float* d_pooled, void* stream) {
     if (!plan || !d_logmel || !d_stats || !d_pooled) return fail(HLMC_ERR_PARAM, "null argument");
     if (B <= 0 || T <= 0) return HLMC_OK;
     CK(cudaSetDevice(plan->device));
-    CK(launch_pool(d_logmel, d_mfcc, d_stats, B, plan->p.n_mels, plan->p.n_mfcc, (int)T, d_pooled,
+    CK(launch_pool(d_logmel, d_mfcc, d_stats, d_chroma, B, plan->p.n_mels, plan->p.n_mfcc, (int)T, d_pooled,
                    static_cast<cudaStream_t>(stream)));
     return HLMC_OK;
+}
+
+int hlmc_pool_device(hlmc_plan* plan, const float* d_logmel, const float* d_mfcc, const float* d_stats,
+                     int64_t B, int64_t T, float* d_pooled, void* stream) {
+    return hlmc_pool_device_ex(plan, d_logmel, d_mfcc, d_stats, nullptr, B, T, d_pooled, stream);
 }
 
 int hlmc_fix_frames_device(const float* d_in, float* d_out, int64_t B, int64_t rows, int64_t T,
@@ -628,7 +754,7 @@ int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format,
                                  s.d_stats, s.d_status, s.d_clipmax, s.stream);
         if (rc != HLMC_OK) return rc;
         if (h_pooled) {
-            CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, c, nm, nc, (int)T,
+            CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, nullptr, c, nm, nc, (int)T,
                            s.d_pooled, s.stream));
             CK(cudaMemcpyAsync(h_pooled + done * pooled_w, s.d_pooled, (size_t)c * pooled_w * 4,
                                cudaMemcpyDeviceToHost, s.stream));

@@ -37,7 +37,22 @@ struct FrameArgs {
     int* status;            // (B) or NULL
     unsigned int* clipmax;  // (B) float bits, max of mel power; or NULL
     float* spec;            // (B, F, T, 2) complex STFT (generic kernel only) or NULL
+    // piptrack candidates for chroma_stft's tuning estimate (register-FFT kernel only) or NULL
+    float2* cand;           // (B, cand_cap) (pitch Hz, interpolated magnitude)
+    int* cand_count;        // (B)
+    int cand_cap;           // per clip
+    int pip_klo, pip_khi;   // bins with fmin <= f < fmax
+    float pip_threshold;    // 0.1
 };
+
+struct ChromaArgs {
+    const int* tuning_idx;  // (B) index into the 100 pre-built filterbanks
+    const float* fb_all;    // (100, kChromaFbFloats) lane-major filterbanks
+    float* chroma;          // (B, 12, T)
+};
+constexpr int kChroma = 12;
+constexpr int kChromaFbFloats = kChroma * 32 * 32 + 16;   // [c][j/4][lane][4] + 12 weights of bin 512 (+pad)
+constexpr int kTuningBins = 100;
 
 // Generic-kernel tables (global memory).
 struct GenericTables {
@@ -62,6 +77,10 @@ struct DbArgs {
 // launchers (all asynchronous on `stream`; return cudaError_t)
 cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                int num_sms, cudaStream_t stream);
+cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,
+                               const FastTables& ft, int num_sms, cudaStream_t stream);
+cudaError_t launch_tuning(const float2* cand, const int* cand_count, int cand_cap, long long B,
+                          const double* d_edges, float* tuning, int* tuning_idx, cudaStream_t stream);
 cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, cudaStream_t stream);
 cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream);
 cudaError_t launch_rowmax(const float* in, unsigned int* clipmax, long long B, long long per_clip,
@@ -69,8 +88,8 @@ cudaError_t launch_rowmax(const float* in, unsigned int* clipmax, long long B, l
 cudaError_t launch_power_to_db(const float* in, float* out, const unsigned int* clipmax, long long B,
                                long long per_clip, int ref_mode, float ref_value, float amin,
                                float top_db, cudaStream_t stream);
-cudaError_t launch_pool(const float* logmel, const float* mfcc, const float* stats, long long B,
-                        int n_mels, int n_mfcc, int T, float* pooled, cudaStream_t stream);
+cudaError_t launch_pool(const float* logmel, const float* mfcc, const float* stats, const float* chroma,
+                        long long B, int n_mels, int n_mfcc, int T, float* pooled, cudaStream_t stream);
 cudaError_t launch_fix_frames(const float* in, float* out, long long B, int rows, int T, int fixed,
                               cudaStream_t stream);
 cudaError_t launch_pcm16_to_f32(const int16_t* raw, long long raw_pitch, float* out, long long pitch,

@@ -114,7 +114,8 @@ __device__ __forceinline__ float sample_edge(const float* __restrict__ clip, int
 // then the scratch for the FFT transposes and the mel gather.  There is no
 // CTA-wide barrier after setup.
 // ---------------------------------------------------------------------------
-constexpr int kWarpBufFloats = 2 * (1024 + 64 + 1) + 2;   // padded 1024-bin complex spectrum (>= 32x33 transpose tile)
+constexpr int kWarpBufFloats = 2 * (1024 + 64 + 1) + 2;
+constexpr int kWarpBufFloats4 = (kWarpBufFloats + 3) & ~3;   // padded 1024-bin complex spectrum (>= 32x33 transpose tile)
 
 __host__ __device__ constexpr int pos32(int k) { return fftreg::fft_pos<32>(k); }
 
@@ -145,7 +146,164 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <int NW>
+struct WarpState {
+    float* sc;                 // this warp's shared buffer (TMA landing zone, then scratch)
+    float2* sc2;
+    uint64_t* mbar;
+    uint32_t parity;
+    const float2 *s_win, *s_tw1, *s_tw2;
+    int lane, zw_base, zlo_base, zhi_base, zhi0;
+};
+
+// One frame, from samples to spectrum, shared by the feature kernel and the chroma kernel.
+// On return vr[i] / vi[i] hold |X|^2 / |X| of bin 16*lane + i (i < 16) and of bin
+// 1024 - 16*lane - (i - 16) (i >= 16); p512 / s512 are bin 512; ss = sum of squares of the
+// frame's samples, zc = zero crossings; m0*/m1* are the lane's magnitude moments about the
+// centres of its two 16-bin runs.
+__device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
+                                               float (&vr)[64], float (&vi)[64], float& p512, float& s512,
+                                               float& ss, int& zc, float& m0l, float& m1l, float& m0h,
+                                               float& m1h) {
+    float* const sc = w.sc;
+    float2* const sc2 = w.sc2;
+    uint64_t* const mbar = w.mbar;
+    const float2* const s_win = w.s_win;
+    const float2* const s_tw1 = w.s_tw1;
+    const float2* const s_tw2 = w.s_tw2;
+    const int lane = w.lane, zw_base = w.zw_base, zlo_base = w.zlo_base, zhi_base = w.zhi_base, zhi0 = w.zhi0;
+    const float zthr = a.zcr_thr;
+    uint32_t& parity = w.parity;
+    const int fs = t * a.hop - a.pad;              // first sample of the frame (clip coords)
+    const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
+    const int shift = (int)((addr & 15) >> 2);
+    int zc_edge = -1;
+    int off;
+
+    // ---- stage the frame's samples in this warp's buffer
+    if (interior && !(shift & 1)) {
+        if (lane == 0) {
+            const float* src0 = reinterpret_cast<const float*>(addr & ~uintptr_t(15));
+            const int tot = shift + kFastNfft;
+            const int bulk = tot & ~3;
+            for (int i = bulk; i < tot; ++i) sc[i] = __ldg(src0 + i);     // <= 3 tail floats
+            fence_proxy_async_smem();       // order earlier generic accesses before the async write
+            mbar_arrive_expect_tx(mbar, (uint32_t)bulk * 4u);
+            tma_bulk_g2s(sc, src0, (uint32_t)bulk * 4u, mbar);
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        off = shift;
+    } else {
+        // edge frame (or odd alignment): build the padded frame by hand; ZCR pads with "edge"
+        int zc = 0;
+        unsigned prev_last = 0u;
+        for (int c = 0; c < kFastNfft / 32; ++c) {
+            const int s = fs + 32 * c + lane;
+            sc[32 * c + lane] = sample_padded(clip, a.n, s, a.pad_mode);
+            const unsigned msk = __ballot_sync(FULL, sample_edge(clip, a.n, s) < -zthr);
+            zc += __popc((msk ^ (msk >> 1)) & 0x7fffffffu);
+            if (c > 0) zc += ((msk & 1u) != prev_last) ? 1 : 0;
+            prev_last = msk >> 31;
+        }
+        zc_edge = zc;
+        off = 0;
+        __syncwarp();
+    }
+
+    ss = 0.0f;
+    unsigned za = 0u, zb = 0u;
+
+    // ---- phase 0: frame -> registers; window; RMS and ZCR partials
+    {
+        const float2* xp = reinterpret_cast<const float2*>(sc + off);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float2 x = xp[lane + 32 * j];
+            const float2 w = s_win[lane + 32 * j];
+            ss = fmaf(x.x, x.x, ss);
+            ss = fmaf(x.y, x.y, ss);
+            // sign bit of (x + thr) <=> x < -thr; sample j ends up at bit 31 - j
+            za = __funnelshift_l(__float_as_uint(x.x + zthr), za, 1);
+            zb = __funnelshift_l(__float_as_uint(x.y + zthr), zb, 1);
+            vr[j] = x.x * w.x;
+            vi[j] = x.y * w.y;
+        }
+    }
+    {
+        // pairs (2m, 2m+1) sit in one lane; pairs (2m+1, 2m+2) straddle to the next lane
+        unsigned zn = __shfl_sync(FULL, za, (lane + 1) & 31);
+        unsigned msk = FULL;
+        if (lane == 31) { zn <<= 1; msk = 0xfffffffeu; }
+        zc = __popc(za ^ zb) + __popc((zb ^ zn) & msk);
+        zc = warp_sum_i(zc);
+        if (zc_edge >= 0) zc = zc_edge;
+    }
+    ss = warp_sum(ss);
+    __syncwarp();                       // every lane has its samples: the buffer becomes scratch
+
+    // ---- phase 1: 32-point FFT over n1 (this lane holds z[lane + 32*n1])
+    fftreg::fft_dif<32>(vr, vi);
+
+    // ---- phase 2: inter-pass twiddle W_1024^(lane*k1)
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) {
+        const float2 w = s_tw1[(k1 - 1) * 32 + lane];
+        const int p = pos32(k1);
+        const float xr = vr[p], xi = vi[p];
+        vr[p] = fmaf(xr, w.x, -(xi * w.y));
+        vi[p] = fmaf(xr, w.y, xi * w.x);
+    }
+
+    // ---- phase 3: 32x32 complex transpose through shared memory
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) sc2[lane * 33 + k1] = make_float2(vr[pos32(k1)], vi[pos32(k1)]);
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) { const float2 v = sc2[n2 * 33 + lane]; vr[n2] = v.x; vi[n2] = v.y; }
+    __syncwarp();
+
+    // ---- phase 4: 32-point FFT over n2; lane = k1, bin k = k1 + 32*k2 at pos32(k2)
+    fftreg::fft_dif<32>(vr, vi);
+
+    // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) and their
+    //      mirrors 1024-k
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2)
+        sc2[zw_base + 34 * k2] = make_float2(vr[pos32(k2)], vi[pos32(k2)]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float2 v = sc2[zlo_base + i]; vr[i] = v.x; vi[i] = v.y; }
+    { const float2 v = sc2[zhi0]; vr[16] = v.x; vi[16] = v.y; }
+#pragma unroll
+    for (int i = 1; i < 16; ++i) { const float2 v = sc2[zhi_base - i]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
+    const float2 e512 = sc2[544];
+    __syncwarp();
+
+    // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
+    m0l = 0.f; m1l = 0.f; m0h = 0.f; m1h = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float2 w = s_tw2[i * 32 + lane];
+        const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
+        const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
+        const float tx = fmaf(w.x, dx, -(w.y * dy));
+        const float ty = fmaf(w.x, dy, w.y * dx);
+        const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
+        const float pk = fmaf(ar, ar, ai * ai);
+        const float pm = fmaf(br, br, bi * bi);
+        const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
+        vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
+        const float d = float(i) - 7.5f;
+        m0l += sk; m1l = fmaf(d, sk, m1l);
+        m0h += sm; m1h = fmaf(-d, sm, m1h);
+    }
+    // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
+    p512 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
+    s512 = fast_sqrt(p512);
+}
+
+template <int NW, bool PIP>
 __global__ void __launch_bounds__(NW * 32, 1)
 frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
     extern __shared__ __align__(16) float smem[];
@@ -182,149 +340,23 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     if (g0 >= g1) return;
     int b = (int)(g0 / a.T);
     int t = (int)(g0 - (long long)b * a.T);
-    uint32_t parity = 0;
     float clip_max = 0.0f;
-    const float zthr = a.zcr_thr;
-
+    WarpState w;
+    w.sc = sc; w.sc2 = sc2; w.mbar = mbar; w.parity = 0;
+    w.s_win = s_win; w.s_tw1 = s_tw1; w.s_tw2 = s_tw2; w.lane = lane;
     // per-lane bases of the regroup buffer, layout p(k) = k + k/16 in float2 units: every
-    // access below is base + immediate and conflict-free (17 is odd)
-    const int zw_base = lane + (lane >> 4);              // write: k = lane + 32*k2 -> zw_base + 34*k2
-    const int zlo_base = 17 * lane;                      // read:  k = 16*lane + i  -> zlo_base + i
-    const int zhi_base = 17 * (63 - lane) + 16;          // read:  k = 1024-16*lane-i (i>=1) -> zhi_base - i
-    const int zhi0 = (lane == 0) ? 0 : 17 * (64 - lane); // read:  k = (1024-16*lane) mod 1024
+    // access is base + immediate and conflict-free (17 is odd)
+    w.zw_base = lane + (lane >> 4);              // write: k = lane + 32*k2 -> zw_base + 34*k2
+    w.zlo_base = 17 * lane;                      // read:  k = 16*lane + i  -> zlo_base + i
+    w.zhi_base = 17 * (63 - lane) + 16;          // read:  k = 1024-16*lane-i (i>=1) -> zhi_base - i
+    w.zhi0 = (lane == 0) ? 0 : 17 * (64 - lane); // read:  k = (1024-16*lane) mod 1024
 
     for (long long g = g0; g < g1; ++g) {
         const float* clip = a.wave + (long long)b * a.pitch;
-        const int fs = t * a.hop - a.pad;              // first sample of the frame (clip coords)
-        const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
-        const int shift = (int)((addr & 15) >> 2);
-        int zc_edge = -1;
-        int off;
-
-        // ---- stage the frame's samples in this warp's buffer
-        if (interior && !(shift & 1)) {
-            if (lane == 0) {
-                const float* src0 = reinterpret_cast<const float*>(addr & ~uintptr_t(15));
-                const int tot = shift + kFastNfft;
-                const int bulk = tot & ~3;
-                for (int i = bulk; i < tot; ++i) sc[i] = __ldg(src0 + i);     // <= 3 tail floats
-                fence_proxy_async_smem();       // order earlier generic accesses before the async write
-                mbar_arrive_expect_tx(mbar, (uint32_t)bulk * 4u);
-                tma_bulk_g2s(sc, src0, (uint32_t)bulk * 4u, mbar);
-            }
-            mbar_wait(mbar, parity);
-            parity ^= 1u;
-            off = shift;
-        } else {
-            // edge frame (or odd alignment): build the padded frame by hand; ZCR pads with "edge"
-            int zc = 0;
-            unsigned prev_last = 0u;
-            for (int c = 0; c < kFastNfft / 32; ++c) {
-                const int s = fs + 32 * c + lane;
-                sc[32 * c + lane] = sample_padded(clip, a.n, s, a.pad_mode);
-                const unsigned msk = __ballot_sync(FULL, sample_edge(clip, a.n, s) < -zthr);
-                zc += __popc((msk ^ (msk >> 1)) & 0x7fffffffu);
-                if (c > 0) zc += ((msk & 1u) != prev_last) ? 1 : 0;
-                prev_last = msk >> 31;
-            }
-            zc_edge = zc;
-            off = 0;
-            __syncwarp();
-        }
-
         float vr[64], vi[64];
-        float ss = 0.0f;
-        unsigned za = 0u, zb = 0u;
-
-        // ---- phase 0: frame -> registers; window; RMS and ZCR partials
-        {
-            const float2* xp = reinterpret_cast<const float2*>(sc + off);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float2 x = xp[lane + 32 * j];
-                const float2 w = s_win[lane + 32 * j];
-                ss = fmaf(x.x, x.x, ss);
-                ss = fmaf(x.y, x.y, ss);
-                // sign bit of (x + thr) <=> x < -thr; sample j ends up at bit 31 - j
-                za = __funnelshift_l(__float_as_uint(x.x + zthr), za, 1);
-                zb = __funnelshift_l(__float_as_uint(x.y + zthr), zb, 1);
-                vr[j] = x.x * w.x;
-                vi[j] = x.y * w.y;
-            }
-        }
+        float p512, s512, ss, m0l, m1l, m0h, m1h;
         int zc;
-        {
-            // pairs (2m, 2m+1) sit in one lane; pairs (2m+1, 2m+2) straddle to the next lane
-            unsigned zn = __shfl_sync(FULL, za, (lane + 1) & 31);
-            unsigned msk = FULL;
-            if (lane == 31) { zn <<= 1; msk = 0xfffffffeu; }
-            zc = __popc(za ^ zb) + __popc((zb ^ zn) & msk);
-            zc = warp_sum_i(zc);
-            if (zc_edge >= 0) zc = zc_edge;
-        }
-        ss = warp_sum(ss);
-        __syncwarp();                       // every lane has its samples: the buffer becomes scratch
-
-        // ---- phase 1: 32-point FFT over n1 (this lane holds z[lane + 32*n1])
-        fftreg::fft_dif<32>(vr, vi);
-
-        // ---- phase 2: inter-pass twiddle W_1024^(lane*k1)
-#pragma unroll
-        for (int k1 = 1; k1 < 32; ++k1) {
-            const float2 w = s_tw1[(k1 - 1) * 32 + lane];
-            const int p = pos32(k1);
-            const float xr = vr[p], xi = vi[p];
-            vr[p] = fmaf(xr, w.x, -(xi * w.y));
-            vi[p] = fmaf(xr, w.y, xi * w.x);
-        }
-
-        // ---- phase 3: 32x32 complex transpose through shared memory
-#pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) sc2[lane * 33 + k1] = make_float2(vr[pos32(k1)], vi[pos32(k1)]);
-        __syncwarp();
-#pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) { const float2 v = sc2[n2 * 33 + lane]; vr[n2] = v.x; vi[n2] = v.y; }
-        __syncwarp();
-
-        // ---- phase 4: 32-point FFT over n2; lane = k1, bin k = k1 + 32*k2 at pos32(k2)
-        fftreg::fft_dif<32>(vr, vi);
-
-        // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) and their
-        //      mirrors 1024-k
-#pragma unroll
-        for (int k2 = 0; k2 < 32; ++k2)
-            sc2[zw_base + 34 * k2] = make_float2(vr[pos32(k2)], vi[pos32(k2)]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { const float2 v = sc2[zlo_base + i]; vr[i] = v.x; vi[i] = v.y; }
-        { const float2 v = sc2[zhi0]; vr[16] = v.x; vi[16] = v.y; }
-#pragma unroll
-        for (int i = 1; i < 16; ++i) { const float2 v = sc2[zhi_base - i]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
-        const float2 e512 = sc2[544];
-        __syncwarp();
-
-        // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
-        float m0l = 0.f, m1l = 0.f, m0h = 0.f, m1h = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 w = s_tw2[i * 32 + lane];
-            const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
-            const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
-            const float tx = fmaf(w.x, dx, -(w.y * dy));
-            const float ty = fmaf(w.x, dy, w.y * dx);
-            const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
-            const float pk = fmaf(ar, ar, ai * ai);
-            const float pm = fmaf(br, br, bi * bi);
-            const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
-            vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
-            const float d = float(i) - 7.5f;
-            m0l += sk; m1l = fmaf(d, sk, m1l);
-            m0h += sm; m1h = fmaf(-d, sm, m1h);
-        }
-        // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
-        const float p512 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
-        const float s512 = fast_sqrt(p512);
+        frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m0h, m1h);
 
         // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
         const float kcl = 16.0f * lane + 7.5f;
@@ -420,6 +452,41 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         if (lane < 16) sc[1089 + lane] = 0.0f;    // zero-weight taps past bin 1024 must read finite values
         __syncwarp();
 
+        // ---- optional: librosa.piptrack candidates for chroma_stft's tuning estimate
+        //      (parabolic interpolation at thresholded local maxima of the power spectrum)
+        if (PIP) {
+            float pmax = p512;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pmax = fmaxf(pmax, vr[i]);
+            pmax = warp_max(pmax);
+            const float ref = a.pip_threshold * pmax;
+            for (int k0 = a.pip_klo; k0 < a.pip_khi; k0 += 32) {
+                const int k = k0 + lane;
+                const bool in = k < a.pip_khi;
+                const int kk = in ? k : a.pip_klo;
+                const float pm1 = sc[(kk - 1) + ((kk - 1) >> 4)];
+                const float p0 = sc[kk + (kk >> 4)];
+                const float pp1 = sc[(kk + 1) + ((kk + 1) >> 4)];
+                const float xm = (pm1 > ref) ? pm1 : 0.0f, x0 = (p0 > ref) ? p0 : 0.0f, xp = (pp1 > ref) ? pp1 : 0.0f;
+                const bool peak = in && (x0 > xm) && (x0 >= xp);
+                const unsigned bal = __ballot_sync(FULL, peak);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(a.cand_count + b, __popc(bal));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (peak) {
+                        const float avg = (pp1 - pm1) * 0.5f;
+                        const float aa = (pp1 + pm1) - 2.0f * p0;
+                        const float shift = (fabsf(avg) >= fabsf(aa)) ? 0.0f : -avg / aa;
+                        const float pitch = (float(k) + shift) * a.binhz;
+                        const float mag = p0 + (0.5f * avg) * shift;
+                        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                        if (slot < a.cand_cap) a.cand[(size_t)b * a.cand_cap + slot] = make_float2(pitch, mag);
+                    }
+                }
+            }
+        }
+
         // ---- phase 8: banded mel projection (librosa.feature.melspectrogram's einsum);
         //      start offsets were shifted on the host so that the 32 lanes hit 32 banks
         if (a.mel_out != nullptr) {
@@ -481,29 +548,220 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     }
 }
 
-template <int NW>
+template <int NW, bool PIP>
 static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                   int num_sms, cudaStream_t stream) {
     const int smem = fast_smem_bytes(ft, NW, a.n_fft, a.hop, a.n_mels);
-    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW>,
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long frames = (long long)a.B * a.T;
     if (frames <= 0) return cudaSuccess;
     long long grid = (frames + NW - 1) / NW;
     if (grid > num_sms) grid = num_sms;
-    frames_fast_2048<NW><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    frames_fast_2048<NW, PIP><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                int num_sms, cudaStream_t stream) {
+    const bool pip = (a.cand != nullptr);
     if (fast_smem_bytes(ft, 16, a.n_fft, a.hop, a.n_mels) <= 227 * 1024)
-        return launch_fast_nw<16>(a, d_tables, ft, num_sms, stream);
+        return pip ? launch_fast_nw<16, true>(a, d_tables, ft, num_sms, stream)
+                   : launch_fast_nw<16, false>(a, d_tables, ft, num_sms, stream);
     if (fast_smem_bytes(ft, 8, a.n_fft, a.hop, a.n_mels) <= 227 * 1024)
-        return launch_fast_nw<8>(a, d_tables, ft, num_sms, stream);
+        return pip ? launch_fast_nw<8, true>(a, d_tables, ft, num_sms, stream)
+                   : launch_fast_nw<8, false>(a, d_tables, ft, num_sms, stream);
     return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------
+// librosa.estimate_tuning on the piptrack candidates: median of the magnitudes (exact, by a
+// three-level radix select on the float bits), then the 100-bin histogram of the pitch
+// residuals of the candidates at or above the median; the tuning is the left edge of the
+// fullest bin.  One CTA per clip.
+// ---------------------------------------------------------------------------
+constexpr int kTunThreads = 256;
+
+__device__ unsigned select_kth_bits(const float2* __restrict__ c, int n, unsigned k, unsigned* hist,
+                                    unsigned* s_misc) {
+    // keys: IEEE bits of the (positive) magnitudes; digits of 11 + 11 + 10 bits
+    unsigned prefix = 0u, mask = 0u;
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        const int sh = shifts[lvl], nb = 1 << widths[lvl];
+        for (int i = threadIdx.x; i < nb; i += kTunThreads) hist[i] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kTunThreads) {
+            const unsigned key = __float_as_uint(c[i].y);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned cum = 0u;
+            int d = 0;
+            for (; d < nb; ++d) {
+                if (cum + hist[d] > k) break;
+                cum += hist[d];
+            }
+            s_misc[0] = (unsigned)d;
+            s_misc[1] = k - cum;
+        }
+        __syncthreads();
+        prefix |= s_misc[0] << sh;
+        mask |= (unsigned)(nb - 1) << sh;
+        k = s_misc[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(kTunThreads)
+tuning_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
+              const double* __restrict__ edges, float* __restrict__ tuning, int* __restrict__ tuning_idx) {
+    __shared__ unsigned hist[2048];
+    __shared__ unsigned s_misc[2];
+    __shared__ unsigned counts[kTuningBins];
+    const long long b = blockIdx.x;
+    const float2* c = cand + (size_t)b * cand_cap;
+    int n = cand_count[b];
+    if (n > cand_cap) n = cand_cap;
+    if (n <= 0) {            // pitch_tuning: no pitches -> 0.0 (bin 50 of linspace(-0.5, 0.5, 101))
+        if (threadIdx.x == 0) { if (tuning) tuning[b] = 0.0f; tuning_idx[b] = kTuningBins / 2; }
+        return;
+    }
+    // np.median
+    const unsigned hi_bits = select_kth_bits(c, n, (unsigned)(n / 2), hist, s_misc);
+    float thr = __uint_as_float(hi_bits);
+    if ((n & 1) == 0) {
+        const unsigned lo_bits = select_kth_bits(c, n, (unsigned)(n / 2 - 1), hist, s_misc);
+        thr = (__uint_as_float(lo_bits) + thr) * 0.5f;
+    }
+    for (int i = threadIdx.x; i < kTuningBins; i += kTunThreads) counts[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kTunThreads) {
+        const float2 pm = c[i];
+        if (!(pm.y >= thr)) continue;
+        // residual of 12 * log2(f / 27.5) modulo one semitone, folded to [-0.5, 0.5)
+        float r = 12.0f * log2f(pm.x / 27.5f);
+        r = r - floorf(r);
+        if (r >= 0.5f) r -= 1.0f;
+        // np.histogram with 100 uniform bins on [-0.5, 0.5]
+        const double x = (double)r;
+        int idx = (int)((x - edges[0]) / (edges[kTuningBins] - edges[0]) * (double)kTuningBins);
+        if (idx >= kTuningBins) idx = kTuningBins - 1;
+        if (idx < 0) idx = 0;
+        if (x < edges[idx] && idx > 0) --idx;
+        else if (idx != kTuningBins - 1 && x >= edges[idx + 1]) ++idx;
+        atomicAdd(&counts[idx], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int i = 1; i < kTuningBins; ++i)
+            if (counts[i] > counts[best]) best = i;
+        if (tuning) tuning[b] = (float)edges[best];
+        tuning_idx[b] = best;
+    }
+}
+cudaError_t launch_tuning(const float2* cand, const int* cand_count, int cand_cap, long long B,
+                          const double* d_edges, float* tuning, int* tuning_idx, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    tuning_kernel<<<(unsigned)B, kTunThreads, 0, stream>>>(cand, cand_count, cand_cap, d_edges, tuning, tuning_idx);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// librosa.feature.chroma_stft: chroma filterbank (of the clip's estimated tuning) applied to
+// the power spectrogram, every frame divided by its largest chroma bin.  A CTA works on one
+// clip at a time so that the clip's 12 x 1025 filterbank sits in shared memory; its warps
+// take the clip's frames round-robin through the same frame_spectrum() front end.
+// ---------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict__ g_tables,
+                 const FastTables ft) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NT = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntab = ft.mel_meta;                      // window + both twiddle tables only
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
+    float* tab = smem + ((2 * NW + 3) & ~3);
+    float* fbs = tab + ntab;                           // this clip's filterbank
+    float* sc = fbs + kChromaFbFloats + warp * kWarpBufFloats4;
+    for (int i = tid; i < ntab / 4; i += NT)
+        reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
+    for (int i = tid; i < NW * kWarpBufFloats4; i += NT) (fbs + kChromaFbFloats)[i] = 0.0f;
+    if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncthreads();
+
+    WarpState w;
+    w.sc = sc; w.sc2 = reinterpret_cast<float2*>(sc); w.mbar = mbar; w.parity = 0;
+    w.s_win = reinterpret_cast<const float2*>(tab + ft.win);
+    w.s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
+    w.s_tw2 = reinterpret_cast<const float2*>(tab + ft.tw2);
+    w.lane = lane;
+    w.zw_base = lane + (lane >> 4);
+    w.zlo_base = 17 * lane;
+    w.zhi_base = 17 * (63 - lane) + 16;
+    w.zhi0 = (lane == 0) ? 0 : 17 * (64 - lane);
+
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const float* src = ca.fb_all + (size_t)ca.tuning_idx[b] * kChromaFbFloats;
+        for (int i = tid; i < kChromaFbFloats / 4; i += NT)
+            reinterpret_cast<float4*>(fbs)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        __syncthreads();
+        const float* clip = a.wave + (long long)b * a.pitch;
+        for (int t = warp; t < a.T; t += NW) {
+            float vr[64], vi[64];
+            float p512, s512, ss, m0l, m1l, m0h, m1h;
+            int zc;
+            frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m0h, m1h);
+            float raw[kChroma];
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) {
+                const float4* fp = reinterpret_cast<const float4*>(fbs) + (c * 8) * 32 + lane;
+                float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 f = fp[j4 * 32];
+                    a0 = fmaf(f.x, vr[4 * j4 + 0], a0);
+                    a1 = fmaf(f.y, vr[4 * j4 + 1], a1);
+                    a0 = fmaf(f.z, vr[4 * j4 + 2], a0);
+                    a1 = fmaf(f.w, vr[4 * j4 + 3], a1);
+                }
+                float r = a0 + a1;
+                if (lane == 31) r = fmaf(fbs[kChroma * 32 * 32 + c], p512, r);
+                raw[c] = warp_sum(r);
+            }
+            float mx = 0.0f;
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) mx = fmaxf(mx, fabsf(raw[c]));
+            const float inv = (mx < 1.17549435e-38f) ? 1.0f : 1.0f / mx;   // util.normalize(norm=inf)
+            float mine = raw[0];
+#pragma unroll
+            for (int c = 1; c < kChroma; ++c) mine = (lane == c) ? raw[c] : mine;
+            if (lane < kChroma) ca.chroma[((size_t)b * kChroma + lane) * a.T + t] = mine * inv;
+            __syncwarp();
+        }
+        __syncthreads();                       // the filterbank is replaced for the next clip
+    }
+}
+
+cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,
+                               const FastTables& ft, int num_sms, cudaStream_t stream) {
+    constexpr int NW = 16;
+    const int smem = (((2 * NW + 3) & ~3) + ft.mel_meta + kChromaFbFloats + NW * kWarpBufFloats4) * 4;
+    cudaError_t e = cudaFuncSetAttribute(chroma_fast_2048<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    if (a.B <= 0) return cudaSuccess;
+    const int grid = a.B < num_sms ? a.B : num_sms;
+    chroma_fast_2048<NW><<<grid, NW * 32, smem, stream>>>(a, c, d_tables, ft);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
@@ -811,9 +1069,9 @@ cudaError_t launch_power_to_db(const float* in, float* out, const unsigned int* 
 // ([R] src/1_preprocessing.py:115-124, src/1_preprocessing_advanced.py:144-151).
 // ---------------------------------------------------------------------------
 __global__ void pool_kernel(const float* __restrict__ logmel, const float* __restrict__ mfcc,
-                            const float* __restrict__ stats, long long B, int n_mels, int n_mfcc,
-                            int T, float* __restrict__ pooled) {
-    const int rows = n_mels + n_mfcc + 5;
+                            const float* __restrict__ stats, const float* __restrict__ chroma, long long B,
+                            int n_mels, int n_mfcc, int n_chroma, int T, float* __restrict__ pooled) {
+    const int rows = n_mels + n_mfcc + 5 + n_chroma;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= B * rows) return;
@@ -828,10 +1086,14 @@ __global__ void pool_kernel(const float* __restrict__ logmel, const float* __res
         const int c = r - n_mels;
         src = mfcc + ((size_t)b * n_mfcc + c) * T;
         o_mean = 2 * n_mels + c; o_std = 2 * n_mels + n_mfcc + c;
-    } else {
+    } else if (r < n_mels + n_mfcc + 5) {
         const int s = r - n_mels - n_mfcc;
         src = stats + ((size_t)b * 5 + s) * T;
         o_mean = 2 * n_mels + 2 * n_mfcc + 2 * s; o_std = o_mean + 1;
+    } else {
+        const int c = r - n_mels - n_mfcc - 5;
+        src = chroma + ((size_t)b * n_chroma + c) * T;
+        o_mean = 2 * n_mels + 2 * n_mfcc + 10 + c; o_std = o_mean + n_chroma;
     }
     float sum = 0.0f;
     for (int i = lane; i < T; i += 32) sum += src[i];
@@ -841,18 +1103,19 @@ __global__ void pool_kernel(const float* __restrict__ logmel, const float* __res
     for (int i = lane; i < T; i += 32) { const float d = src[i] - mean; var = fmaf(d, d, var); }
     var = warp_sum(var);
     if (lane == 0) {
-        float* out = pooled + (size_t)b * (2 * n_mels + 2 * n_mfcc + 10);
+        float* out = pooled + (size_t)b * (2 * n_mels + 2 * n_mfcc + 10 + 2 * n_chroma);
         out[o_mean] = mean;
         out[o_std] = sqrtf(var / float(T));
     }
 }
-cudaError_t launch_pool(const float* logmel, const float* mfcc, const float* stats, long long B,
-                        int n_mels, int n_mfcc, int T, float* pooled, cudaStream_t stream) {
+cudaError_t launch_pool(const float* logmel, const float* mfcc, const float* stats, const float* chroma,
+                        long long B, int n_mels, int n_mfcc, int T, float* pooled, cudaStream_t stream) {
     if (mfcc == nullptr) n_mfcc = 0;
-    const long long warps = B * (n_mels + n_mfcc + 5);
+    const int n_chroma = chroma ? kChroma : 0;
+    const long long warps = B * (n_mels + n_mfcc + 5 + n_chroma);
     if (warps <= 0) return cudaSuccess;
-    pool_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(logmel, mfcc, stats, B, n_mels, n_mfcc,
-                                                                 T, pooled);
+    pool_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(logmel, mfcc, stats, chroma, B, n_mels,
+                                                                 n_mfcc, n_chroma, T, pooled);
     g_launches++;
     return cudaGetLastError();
 }

@@ -6,10 +6,11 @@ Function names, arguments and return shapes follow
 functions replace the scripts' per-file loop / joblib map with one call.
 
 Chroma: the saved vectors carry 24 ``chroma_stft`` columns
-([R] 1_preprocessing.py:126-127, _advanced.py:153-154) that are outside this
-round's hot path.  They are never computed on a hidden CPU
-path: ``chroma=`` must say what to put there -- ``"zeros"`` (default, logged),
-``"nan"``, or an explicit (B, 24) array the caller computed elsewhere.
+([R] 1_preprocessing.py:126-127, _advanced.py:153-154).  ``chroma="device"``
+(default) computes them on the GPU (librosa.feature.chroma_stft including the
+per-clip tuning estimate); ``"zeros"`` / ``"nan"`` skip that
+second STFT pass and fill the columns (logged), and an explicit (B, 24) array
+is taken as given.  There is never a hidden CPU path.
 """
 from __future__ import annotations
 
@@ -41,6 +42,25 @@ def _basic_extractor(cfg=BASIC_CONFIG, device=0) -> FeatureExtractor:
     # the spectral statistics use librosa's default n_fft=2048 (the scripts do not forward it)
     return get_extractor(sr=cfg["sample_rate"], n_fft=cfg["n_fft"], hop_length=cfg["hop_length"],
                          n_mels=cfg["n_mels"], n_mfcc=cfg.get("n_mfcc", 0), ref=np.max, device=device)
+
+
+def _pooled_on_device(ex, waves, with_chroma, device, chunk_clips):
+    """Chunked device-resident extraction of the pooled feature rows (+ status)."""
+    import torch
+
+    waves = np.ascontiguousarray(waves, dtype=np.float32)
+    B = waves.shape[0]
+    width = ex.pooled_width(ex.n_mfcc > 0, with_chroma)
+    pooled = np.empty((B, width), np.float32)
+    status = np.empty((B,), np.int32)
+    dev = torch.device("cuda", device)
+    for lo in range(0, B, chunk_clips):
+        hi = min(B, lo + chunk_clips)
+        r = ex.extract_device(torch.from_numpy(waves[lo:hi]).to(dev), mfcc=ex.n_mfcc > 0, stats=True,
+                              pooled=True, chroma=with_chroma)
+        pooled[lo:hi] = r["pooled"].cpu().numpy()
+        status[lo:hi] = r["status"].cpu().numpy()
+    return pooled, status
 
 
 def _chroma_block(chroma, B):
@@ -92,8 +112,8 @@ def extract_spectral_features(audio, sr, cfg=BASIC_CONFIG):
             for i, name in enumerate(STAT_NAMES)}
 
 
-def extract_all_features_batch(waves, sr=22050, cfg=BASIC_CONFIG, chroma="zeros", device=0,
-                               return_status=False):
+def extract_all_features_batch(waves, sr=22050, cfg=BASIC_CONFIG, chroma="device", device=0,
+                               return_status=False, chunk_clips=256):
     """Batched [R] 1_preprocessing.py:105-129: (B, n) -> (B, 370) float64.
 
     Columns: mel mean/std (256) | MFCC mean/std (80) | 5 x (mean, std) | chroma (24).
@@ -102,14 +122,25 @@ def extract_all_features_batch(waves, sr=22050, cfg=BASIC_CONFIG, chroma="zeros"
     """
     ex = _basic_extractor(dict(cfg, sample_rate=sr), device=device)
     waves = np.asarray(waves)
-    r = ex.extract_host(waves, logmel=False, mfcc=False, stats=False, pooled=True)
-    feats = np.concatenate([r["pooled"].astype(np.float64), _chroma_block(chroma, waves.shape[0])], axis=1)
-    bad = r["status"] != 0
-    feats[bad] = np.nan
-    return (feats, r["status"]) if return_status else feats
+    if isinstance(chroma, str) and chroma == "device":
+        pooled, status = _pooled_on_device(ex, waves, True, device, chunk_clips)
+        feats = pooled.astype(np.float64)
+    else:
+        r = ex.extract_host(waves, logmel=False, mfcc=False, stats=False, pooled=True)
+        status = r["status"]
+        feats = np.concatenate([r["pooled"].astype(np.float64), _chroma_block(chroma, waves.shape[0])], axis=1)
+    feats[status != 0] = np.nan
+    return (feats, status) if return_status else feats
 
 
-def extract_all_features(audio, sr, cfg=BASIC_CONFIG, chroma="zeros"):
+def extract_chroma_features(audio, sr, cfg=BASIC_CONFIG):
+    """[R] 1_preprocessing.py:94-102 -> (12, T) float32 chroma_stft."""
+    from .api import feature
+
+    return feature.chroma_stft(y=np.asarray(audio), sr=sr, n_fft=cfg["n_fft"], hop_length=cfg["hop_length"])
+
+
+def extract_all_features(audio, sr, cfg=BASIC_CONFIG, chroma="device"):
     """[R] 1_preprocessing.py:105-129 -> (370,) float64."""
     f, status = extract_all_features_batch(np.asarray(audio)[None], sr, cfg, chroma, return_status=True)
     _raise_failed(status)
@@ -119,7 +150,7 @@ def extract_all_features(audio, sr, cfg=BASIC_CONFIG, chroma="zeros"):
 # ---------------------------------------------------------------------------
 # src/1_preprocessing_advanced.py
 # ---------------------------------------------------------------------------
-def process_batch_advanced(waves, sr=22050, cfg=ADV_CONFIG, chroma="zeros", device=0, chunk_clips=64):
+def process_batch_advanced(waves, sr=22050, cfg=ADV_CONFIG, chroma="device", device=0, chunk_clips=64):
     """Batched [R] _advanced.py:97-156 (extract_mel_spectrogram + extract_flattened_features).
 
     (B, n) host float32 -> (mel (B, n_mels, fixed_time_steps) f32, flat (B, 290) f64, status (B,)).
@@ -136,13 +167,14 @@ def process_batch_advanced(waves, sr=22050, cfg=ADV_CONFIG, chroma="zeros", devi
     T = ex.num_frames(n)
     fixed = int(cfg["fixed_time_steps"])
     mel = np.empty((B, ex.n_mels, fixed), np.float32)
-    flat = np.empty((B, 2 * ex.n_mels + 10), np.float32)
+    on_dev = isinstance(chroma, str) and chroma == "device"
+    flat = np.empty((B, 2 * ex.n_mels + 10 + (24 if on_dev else 0)), np.float32)
     status = np.empty((B,), np.int32)
     dev = torch.device("cuda", device)
     for lo in range(0, B, chunk_clips):
         hi = min(B, lo + chunk_clips)
         w = torch.from_numpy(waves[lo:hi]).to(dev, non_blocking=True)
-        r = ex.extract_device(w, mfcc=False, stats=True, pooled=True)
+        r = ex.extract_device(w, mfcc=False, stats=True, pooled=True, chroma=on_dev)
         fx = torch.empty((hi - lo, ex.n_mels, fixed), dtype=torch.float32, device=dev)
         _check(lib.hlmc_fix_frames_device(C.c_void_p(r["logmel"].data_ptr()), C.c_void_p(fx.data_ptr()),
                                           hi - lo, ex.n_mels, T, fixed, device,
@@ -150,7 +182,8 @@ def process_batch_advanced(waves, sr=22050, cfg=ADV_CONFIG, chroma="zeros", devi
         mel[lo:hi] = fx.cpu().numpy()
         flat[lo:hi] = r["pooled"].cpu().numpy()
         status[lo:hi] = r["status"].cpu().numpy()
-    feats = np.concatenate([flat.astype(np.float64), _chroma_block(chroma, B)], axis=1)
+    feats = flat.astype(np.float64) if on_dev else np.concatenate(
+        [flat.astype(np.float64), _chroma_block(chroma, B)], axis=1)
     feats[status != 0] = np.nan
     return mel, feats, status
 
@@ -162,7 +195,7 @@ def extract_mel_spectrogram_fixed(audio, sr, cfg=ADV_CONFIG):
     return mel[0]
 
 
-def extract_flattened_features(audio, sr, cfg=ADV_CONFIG, chroma="zeros"):
+def extract_flattened_features(audio, sr, cfg=ADV_CONFIG, chroma="device"):
     """[R] _advanced.py:120-156 -> (290,) float64."""
     _m, f, status = process_batch_advanced(np.asarray(audio)[None], sr, cfg, chroma)
     _raise_failed(status)

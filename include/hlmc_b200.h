@@ -136,6 +136,19 @@ int hlmc_extract_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t
                         int64_t pitch, float *d_logmel, float *d_mfcc, float *d_stats,
                         int32_t *d_status, float *d_clipmax, void *stream);
 
+/* The same plus librosa.feature.chroma_stft ([R] src/1_preprocessing.py:96-101,
+ * src/1_preprocessing_advanced.py:139-141; n_fft = 2048, power = 2 plans only):
+ *   d_chroma : (B, 12, T) float32, each frame divided by its largest chroma bin, or NULL
+ *   d_tuning : (B) float32, the per-clip librosa.estimate_tuning result, or NULL
+ *   d_work   : hlmc_chroma_workspace_bytes(plan, B, n) bytes of device scratch
+ * The tuning estimate (piptrack candidates -> median magnitude -> 100-bin residual histogram) is
+ * per clip; the chroma filterbank of that tuning comes from 100 filterbanks built at first use.  */
+int64_t hlmc_chroma_workspace_bytes(hlmc_plan *plan, int64_t B, int64_t n);
+int hlmc_extract_device_ex(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t n,
+                           int64_t pitch, float *d_logmel, float *d_mfcc, float *d_stats,
+                           int32_t *d_status, float *d_clipmax, float *d_chroma, float *d_tuning,
+                           void *d_work, int64_t work_bytes, void *stream);
+
 /* Per-kernel timing of hlmc_extract_device for the roofline report: when
  * enabled, CUDA events are recorded on the launching stream around the frames
  * kernel and around the dB+DCT kernel.  hlmc_plan_read_timing synchronises on
@@ -168,6 +181,12 @@ int hlmc_power_to_db_device(const float *d_in, float *d_out, int64_t B, int64_t 
 int hlmc_pool_device(hlmc_plan *plan, const float *d_logmel, const float *d_mfcc,
                      const float *d_stats, int64_t B, int64_t T, float *d_pooled,
                      void *stream);
+
+/* With d_chroma != NULL the pooled row grows by [chroma mean (12) | chroma std (12)]: the full
+ * 370 / 290 column layout of the scripts.                                     */
+int hlmc_pool_device_ex(hlmc_plan *plan, const float *d_logmel, const float *d_mfcc,
+                        const float *d_stats, const float *d_chroma, int64_t B, int64_t T,
+                        float *d_pooled, void *stream);
 
 /* [R] _advanced.py:108-112: crop to fixed_time_steps frames, or right-pad
  * with the clip's minimum.  d_out: (B, rows, fixed) float32.                 */

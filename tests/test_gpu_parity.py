@@ -255,15 +255,17 @@ def test_script_level_functions_and_layout(built, tmp_path):
     f = pp.extract_all_features(y[0], SR)
     want = orc.extract_all_features(y[0], SR, with_chroma=False)
     assert f.shape == (370,) and f.dtype == np.float64
+    assert np.abs(f[346:] - orc.extract_all_features(y[0], SR)[346:]).max() <= 1e-4   # chroma on device
     # pooled means / stds of quantities that each meet the per-frame tolerance; the two
     # rolloff columns may move by a tie flip (one 10.77 Hz bin in one of 130 frames)
     d = np.abs(f[:346] - want)
     tol = 1e-3 + 1e-4 * np.abs(want)
     tol[340:342] = 3 * (SR / 2048)
     assert np.all(d <= tol), np.nonzero(d > tol)
-    assert np.all(f[346:] == 0.0)        # chroma policy "zeros", logged
+    assert np.all(pp.extract_all_features(y[0], SR, chroma="zeros")[346:] == 0.0)   # explicit policy, logged
     fb = pp.extract_all_features_batch(y, SR, chroma="nan")
     assert fb.shape == (5, 370) and np.isnan(fb[:, 346:]).all() and np.array_equal(fb[0, :346], f[:346])
+    fb = pp.extract_all_features_batch(y, SR)
     # 1_preprocessing_advanced.py
     mel, flat, status = pp.process_batch_advanced(y, SR)
     assert mel.shape == (5, 128, 1024) and mel.dtype == np.float32 and flat.shape == (5, 290)
@@ -355,3 +357,43 @@ def test_pcm16_and_device_pad_front_end(built):
     assert_clip(compare_clip({k: a[k][2] for k in ("logmel", "mfcc", "stats")}, want), where="pcm16 clip 2")
     with pytest.raises(hl.ParameterError):
         ex.extract_host(y16, pad_to=100)
+
+
+def test_chroma_stft_and_tuning_on_device(built):
+    """librosa.feature.chroma_stft incl. estimate_tuning (piptrack -> median -> histogram).
+    The tuning is an arg-max over a 100-bin histogram: where the oracle's own histogram has a near tie
+    the device may pick the other bin; that is allowed only in that case."""
+    import torch
+
+    hl = built
+    for n in (22050, 66150):
+        y = hl.synth.synth_batch(20, n, seed=31)
+        ex = hl.FeatureExtractor(n_mfcc=40, ref=np.max)
+        out = ex.extract_device(torch.from_numpy(y).cuda(), chroma=True, pooled=True)
+        ch, tu = out["chroma"].cpu().numpy(), out["tuning"].cpu().numpy()
+        assert out["pooled"].shape == (20, 370)
+        ties = 0
+        for i in range(len(y)):
+            S = np.abs(orc.stft(y[i])) ** 2
+            t_or = orc.estimate_tuning(S=S, sr=SR, n_fft=2048, bins_per_octave=12)
+            if abs(tu[i] - t_or) > 1e-6:
+                p, m = orc.piptrack(S=S, sr=SR, n_fft=2048)
+                sel = p[(m >= np.median(m[p > 0])) & (p > 0)]
+                res = np.mod(12 * np.log2(sel / 27.5), 1.0)
+                res[res >= 0.5] -= 1.0
+                counts, edges = np.histogram(res, np.linspace(-0.5, 0.5, 101))
+                got = int(round((tu[i] + 0.5) * 100))
+                assert counts[got] >= counts.max() - 2, f"tuning {tu[i]} vs {t_or} without a near tie (clip {i})"
+                ties += 1
+            want = orc.chroma_stft(y=y[i], sr=SR, tuning=float(tu[i]))
+            assert ch[i].shape == want.shape == (12, 1 + n // 512)
+            assert np.abs(ch[i] - want).max() <= 1e-4, f"chroma clip {i}"
+            assert ch[i].max() <= 1.0 + 1e-6
+        assert ties <= 2
+        # pooled chroma columns = mean / std over frames
+        po = out["pooled"].cpu().numpy()
+        assert np.abs(po[:, 346:358] - ch.mean(-1)).max() <= 1e-5 and np.abs(po[:, 358:370] - ch.std(-1)).max() <= 1e-5
+    c1 = hl.feature.chroma_stft(y=y[3], sr=SR, n_fft=2048, hop_length=512)
+    assert c1.shape == (12, 130) and np.array_equal(c1, ch[3])
+    with pytest.raises(hl.UnsupportedError):
+        hl.FeatureExtractor(n_fft=1024).extract_device(torch.zeros(1, 8000, device="cuda"), chroma=True)
