@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--clips", type=int, default=10000, help="clips per GPU per step (configs[1]: 10000)")
     ap.add_argument("--seconds", type=float, default=CLIP_SECONDS)
     ap.add_argument("--cpu-sample", type=int, default=0, help="clips in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--chroma", action="store_true", help="also compute chroma_stft (second STFT pass) in every step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -239,7 +240,7 @@ def main():
 
     out = None
     for _ in range(max(3, args.warmup)):
-        out = ex.extract_device(d_wave, out=out)
+        out = ex.extract_device(d_wave, out=out, chroma=args.chroma)
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -254,7 +255,7 @@ def main():
     t_wall0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        out = ex.extract_device(d_wave, out=out)
+        out = ex.extract_device(d_wave, out=out, chroma=args.chroma)
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -378,6 +379,7 @@ def main():
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "clips_per_gpu": B, "samples_per_clip": n, "frames_per_clip": T,
+                   "chroma_stft_included": bool(args.chroma),
                    "l2_policy": "inputs larger than L2 (2.6 GB per step)", "parallelism": f"clips sharded x{world}, no collective"},
         "audio_hours_per_sec": value * args.seconds / 3600.0,
         "e2e": e2e, "e2e_pcm16": e2e_pcm, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,

@@ -505,7 +505,8 @@ int64_t hlmc_chroma_workspace_bytes(hlmc_plan* plan, int64_t B, int64_t n) {
     if (rc != HLMC_OK) return rc;
     const int64_t T = hlmc_num_frames(&plan->p, n);
     if (T < 0) return T;
-    return (int64_t)(2 * align256((size_t)B * 4) + (size_t)B * T * plan->cand_per_frame * sizeof(float2));
+    return (int64_t)(align256((size_t)B * T * 4) + align256((size_t)B * 4) +
+                     (size_t)B * T * plan->cand_per_frame * sizeof(float2));
 }
 
 int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
@@ -529,11 +530,10 @@ int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int6
         const int64_t need = hlmc_chroma_workspace_bytes(plan, B, n);
         if (!d_work || work_bytes < need) return fail(HLMC_ERR_PARAM, "chroma workspace too small");
         char* wsp = static_cast<char*>(d_work);
-        cand_count = reinterpret_cast<int*>(wsp);
-        tuning_idx = reinterpret_cast<int*>(wsp + align256((size_t)B * 4));
-        cand = reinterpret_cast<float2*>(wsp + 2 * align256((size_t)B * 4));
-        cand_cap = (int)(T * plan->cand_per_frame);
-        CK(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
+        cand_count = reinterpret_cast<int*>(wsp);                                   // (B, T), every entry written
+        tuning_idx = reinterpret_cast<int*>(wsp + align256((size_t)B * T * 4));
+        cand = reinterpret_cast<float2*>(wsp + align256((size_t)B * T * 4) + align256((size_t)B * 4));
+        cand_cap = plan->cand_per_frame;
     }
     cudaEvent_t ev3[3] = {nullptr, nullptr, nullptr};
     if (plan->timing) {
@@ -556,7 +556,7 @@ int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int6
         for (auto& e : ev3) plan->ev.push_back(e);
     }
     if (d_chroma) {
-        CK(launch_tuning(cand, cand_count, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
+        CK(launch_tuning(cand, cand_count, (int)T, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
         FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
         ChromaArgs ca{tuning_idx, plan->d_chroma_fb, d_chroma};
         CK(launch_chroma_fast(a, ca, plan->d_fast, plan->ft, plan->num_sms, st));

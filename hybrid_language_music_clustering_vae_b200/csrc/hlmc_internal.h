@@ -38,9 +38,9 @@ struct FrameArgs {
     unsigned int* clipmax;  // (B) float bits, max of mel power; or NULL
     float* spec;            // (B, F, T, 2) complex STFT (generic kernel only) or NULL
     // piptrack candidates for chroma_stft's tuning estimate (register-FFT kernel only) or NULL
-    float2* cand;           // (B, cand_cap) (pitch Hz, interpolated magnitude)
-    int* cand_count;        // (B)
-    int cand_cap;           // per clip
+    float2* cand;           // (B, T, cand_cap) (pitch Hz, interpolated magnitude)
+    int* cand_count;        // (B, T)
+    int cand_cap;           // slots per frame
     int pip_klo, pip_khi;   // bins with fmin <= f < fmax
     float pip_threshold;    // 0.1
 };
@@ -79,7 +79,7 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
                                int num_sms, cudaStream_t stream);
 cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,
                                const FastTables& ft, int num_sms, cudaStream_t stream);
-cudaError_t launch_tuning(const float2* cand, const int* cand_count, int cand_cap, long long B,
+cudaError_t launch_tuning(const float2* cand, const int* cand_count, int T, int cand_per_frame, long long B,
                           const double* d_edges, float* tuning, int* tuning_idx, cudaStream_t stream);
 cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, cudaStream_t stream);
 cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream);

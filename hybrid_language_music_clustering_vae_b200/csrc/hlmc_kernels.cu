@@ -460,6 +460,10 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             for (int i = 0; i < 32; ++i) pmax = fmaxf(pmax, vr[i]);
             pmax = warp_max(pmax);
             const float ref = a.pip_threshold * pmax;
+            // every frame owns a fixed block of cand_cap slots (at most every other bin of the band
+            // can be a peak), so no atomics are needed; the count goes to cand_count[b*T + t]
+            float2* slots = a.cand + ((size_t)b * a.T + t) * a.cand_cap;
+            int base = 0;
             for (int k0 = a.pip_klo; k0 < a.pip_khi; k0 += 32) {
                 const int k = k0 + lane;
                 const bool in = k < a.pip_khi;
@@ -470,21 +474,18 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 const float xm = (pm1 > ref) ? pm1 : 0.0f, x0 = (p0 > ref) ? p0 : 0.0f, xp = (pp1 > ref) ? pp1 : 0.0f;
                 const bool peak = in && (x0 > xm) && (x0 >= xp);
                 const unsigned bal = __ballot_sync(FULL, peak);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(a.cand_count + b, __popc(bal));
-                    base = __shfl_sync(FULL, base, 0);
-                    if (peak) {
-                        const float avg = (pp1 - pm1) * 0.5f;
-                        const float aa = (pp1 + pm1) - 2.0f * p0;
-                        const float shift = (fabsf(avg) >= fabsf(aa)) ? 0.0f : -avg / aa;
-                        const float pitch = (float(k) + shift) * a.binhz;
-                        const float mag = p0 + (0.5f * avg) * shift;
-                        const int slot = base + __popc(bal & ((1u << lane) - 1u));
-                        if (slot < a.cand_cap) a.cand[(size_t)b * a.cand_cap + slot] = make_float2(pitch, mag);
-                    }
+                if (peak) {
+                    const float avg = (pp1 - pm1) * 0.5f;
+                    const float aa = (pp1 + pm1) - 2.0f * p0;
+                    const float shift = (fabsf(avg) >= fabsf(aa)) ? 0.0f : -avg / aa;
+                    const float pitch = (float(k) + shift) * a.binhz;
+                    const float mag = p0 + (0.5f * avg) * shift;
+                    const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < a.cand_cap) slots[slot] = make_float2(pitch, mag);
                 }
+                base += __popc(bal);
             }
+            if (lane == 0) a.cand_count[(size_t)b * a.T + t] = min(base, a.cand_cap);
         }
 
         // ---- phase 8: banded mel projection (librosa.feature.melspectrogram's einsum);
@@ -584,8 +585,20 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
 // ---------------------------------------------------------------------------
 constexpr int kTunThreads = 256;
 
-__device__ unsigned select_kth_bits(const float2* __restrict__ c, int n, unsigned k, unsigned* hist,
-                                    unsigned* s_misc) {
+// Walks every candidate of the clip: one warp per frame, lanes over that frame's list.
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const float2* __restrict__ c, const int* __restrict__ cnt,
+                                                   int T, int cpf, F f) {
+    const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int t = wp; t < T; t += kTunThreads / 32) {
+        const int m = cnt[t];
+        const float2* row = c + (size_t)t * cpf;
+        for (int j = ln; j < m; j += 32) f(row[j]);
+    }
+}
+
+__device__ unsigned select_kth_bits(const float2* __restrict__ c, const int* __restrict__ cnt, int T, int cpf,
+                                    unsigned k, unsigned* hist, unsigned* s_misc, unsigned* s_warp) {
     // keys: IEEE bits of the (positive) magnitudes; digits of 11 + 11 + 10 bits
     unsigned prefix = 0u, mask = 0u;
     const int shifts[3] = {21, 10, 0};
@@ -594,20 +607,39 @@ __device__ unsigned select_kth_bits(const float2* __restrict__ c, int n, unsigne
         const int sh = shifts[lvl], nb = 1 << widths[lvl];
         for (int i = threadIdx.x; i < nb; i += kTunThreads) hist[i] = 0u;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += kTunThreads) {
-            const unsigned key = __float_as_uint(c[i].y);
+        for_each_candidate(c, cnt, T, cpf, [&](const float2 pm) {
+            const unsigned key = __float_as_uint(pm.y);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
-        }
+        });
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned cum = 0u;
-            int d = 0;
-            for (; d < nb; ++d) {
-                if (cum + hist[d] > k) break;
-                cum += hist[d];
+        // digit search: every thread owns nb/256 consecutive bins; block-wide exclusive scan of the
+        // per-thread sums (warp shuffles + one shared hop), then the owner of rank k walks its bins
+        {
+            const int per = nb / kTunThreads;                 // 8 or 4
+            unsigned mine = 0u;
+            for (int j = 0; j < per; ++j) mine += hist[threadIdx.x * per + j];
+            unsigned incl = mine;
+            const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned tv = __shfl_up_sync(FULL, incl, d);
+                if (ln >= d) incl += tv;
             }
-            s_misc[0] = (unsigned)d;
-            s_misc[1] = k - cum;
+            if (ln == 31) s_warp[wp] = incl;
+            __syncthreads();
+            unsigned off = 0u;
+            for (int q = 0; q < wp; ++q) off += s_warp[q];
+            const unsigned excl = off + incl - mine;
+            if (k >= excl && k < excl + mine) {
+                unsigned cum = excl;
+                int d = threadIdx.x * per;
+                for (;; ++d) {
+                    if (cum + hist[d] > k) break;
+                    cum += hist[d];
+                }
+                s_misc[0] = (unsigned)d;
+                s_misc[1] = k - cum;
+            }
         }
         __syncthreads();
         prefix |= s_misc[0] << sh;
@@ -619,31 +651,41 @@ __device__ unsigned select_kth_bits(const float2* __restrict__ c, int n, unsigne
 }
 
 __global__ void __launch_bounds__(kTunThreads)
-tuning_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
+tuning_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_count, int T, int cpf,
               const double* __restrict__ edges, float* __restrict__ tuning, int* __restrict__ tuning_idx) {
     __shared__ unsigned hist[2048];
     __shared__ unsigned s_misc[2];
+    __shared__ unsigned s_warp[kTunThreads / 32];
     __shared__ unsigned counts[kTuningBins];
+    __shared__ int s_n;
     const long long b = blockIdx.x;
-    const float2* c = cand + (size_t)b * cand_cap;
-    int n = cand_count[b];
-    if (n > cand_cap) n = cand_cap;
+    const float2* c = cand + (size_t)b * T * cpf;
+    const int* cnt = cand_count + (size_t)b * T;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    {
+        int part = 0;
+        for (int t = threadIdx.x; t < T; t += kTunThreads) part += cnt[t];
+        part = warp_sum_i(part);
+        if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_n, part);
+    }
+    __syncthreads();
+    const int n = s_n;
     if (n <= 0) {            // pitch_tuning: no pitches -> 0.0 (bin 50 of linspace(-0.5, 0.5, 101))
         if (threadIdx.x == 0) { if (tuning) tuning[b] = 0.0f; tuning_idx[b] = kTuningBins / 2; }
         return;
     }
     // np.median
-    const unsigned hi_bits = select_kth_bits(c, n, (unsigned)(n / 2), hist, s_misc);
+    const unsigned hi_bits = select_kth_bits(c, cnt, T, cpf, (unsigned)(n / 2), hist, s_misc, s_warp);
     float thr = __uint_as_float(hi_bits);
     if ((n & 1) == 0) {
-        const unsigned lo_bits = select_kth_bits(c, n, (unsigned)(n / 2 - 1), hist, s_misc);
+        const unsigned lo_bits = select_kth_bits(c, cnt, T, cpf, (unsigned)(n / 2 - 1), hist, s_misc, s_warp);
         thr = (__uint_as_float(lo_bits) + thr) * 0.5f;
     }
     for (int i = threadIdx.x; i < kTuningBins; i += kTunThreads) counts[i] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kTunThreads) {
-        const float2 pm = c[i];
-        if (!(pm.y >= thr)) continue;
+    for_each_candidate(c, cnt, T, cpf, [&](const float2 pm) {
+        if (!(pm.y >= thr)) return;
         // residual of 12 * log2(f / 27.5) modulo one semitone, folded to [-0.5, 0.5)
         float r = 12.0f * log2f(pm.x / 27.5f);
         r = r - floorf(r);
@@ -656,7 +698,7 @@ tuning_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_coun
         if (x < edges[idx] && idx > 0) --idx;
         else if (idx != kTuningBins - 1 && x >= edges[idx + 1]) ++idx;
         atomicAdd(&counts[idx], 1u);
-    }
+    });
     __syncthreads();
     if (threadIdx.x == 0) {
         int best = 0;
@@ -666,10 +708,11 @@ tuning_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_coun
         tuning_idx[b] = best;
     }
 }
-cudaError_t launch_tuning(const float2* cand, const int* cand_count, int cand_cap, long long B,
+cudaError_t launch_tuning(const float2* cand, const int* cand_count, int T, int cand_per_frame, long long B,
                           const double* d_edges, float* tuning, int* tuning_idx, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    tuning_kernel<<<(unsigned)B, kTunThreads, 0, stream>>>(cand, cand_count, cand_cap, d_edges, tuning, tuning_idx);
+    tuning_kernel<<<(unsigned)B, kTunThreads, 0, stream>>>(cand, cand_count, T, cand_per_frame, d_edges, tuning,
+                                                           tuning_idx);
     g_launches++;
     return cudaGetLastError();
 }
