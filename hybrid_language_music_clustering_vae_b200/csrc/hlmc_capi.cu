@@ -36,6 +36,7 @@ struct HostPipeSlot {
     float* d_stats = nullptr; float* d_pooled = nullptr; float* d_clipmax = nullptr;
     int32_t* d_status = nullptr;
     int16_t* d_raw = nullptr; size_t raw_elems = 0;     // PCM16 staging (hlmc_extract_host_ex)
+    float* d_melscr = nullptr;                           // frame-major mel-power scratch
 };
 
 struct hlmc_plan {
@@ -233,7 +234,7 @@ void hlmc_plan_destroy(hlmc_plan* plan) {
     for (auto& s : plan->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(plan->d_fast); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
@@ -260,6 +261,13 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
     hlmc_plan* pl = new hlmc_plan();
     pl->p = p; pl->device = device; pl->F = p.n_fft / 2 + 1;
     cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
+    {   // the per-call mel scratch comes from the stream-ordered pool: do not hand it back at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     const char* fg = getenv("HLMC_FORCE_GENERIC");
     pl->force_generic = (fg && fg[0] == '1') ? 1 : 0;
     const int N = p.n_fft, M = N / 2, F = pl->F;
@@ -468,9 +476,10 @@ static FrameArgs make_frame_args(const hlmc_plan* pl, const float* d_wave, int64
 
 static int run_frames(hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, int64_t pitch, int T,
                       float* d_mel, float* d_stats, int32_t* d_status, float* d_clipmax, float* d_spec,
-                      cudaStream_t st, float2* cand = nullptr, int* cand_count = nullptr, int cand_cap = 0) {
+                      cudaStream_t st, float2* cand = nullptr, int* cand_count = nullptr, int cand_cap = 0,
+                      int mel_frame_major = 0) {
     FrameArgs a = make_frame_args(pl, d_wave, B, n, pitch, T);
-    a.mel_out = d_mel; a.stats = d_stats; a.status = d_status;
+    a.mel_out = d_mel; a.stats = d_stats; a.status = d_status; a.mel_frame_major = mel_frame_major;
     a.clipmax = reinterpret_cast<unsigned int*>(d_clipmax); a.spec = d_spec;
     a.cand = cand; a.cand_count = cand_count; a.cand_cap = cand_cap;
     if (d_clipmax) CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));
@@ -509,10 +518,10 @@ int64_t hlmc_chroma_workspace_bytes(hlmc_plan* plan, int64_t B, int64_t n) {
                      (size_t)B * T * plan->cand_per_frame * sizeof(float2));
 }
 
-int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
-                           float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
-                           float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
-                           int64_t work_bytes, void* stream) {
+static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                               float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
+                               float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
+                               int64_t work_bytes, void* stream, float* d_melscr) {
     int64_t T;
     int rc = check_batch(plan, d_wave, B, n, pitch, &T);
     if (rc != HLMC_OK) return rc;
@@ -541,12 +550,19 @@ int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int6
         CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));   // keep the memsets out of the bracket
     }
     if (plan->timing) CK(cudaEventRecord(ev3[0], st));
-    rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_logmel, d_stats, d_status, d_clipmax, nullptr, st,
-                    cand, cand_count, cand_cap);
+    // The frames kernel writes the mel power frame-major (each frame's n_mels values contiguous:
+    // full-sector coalesced stores) into a scratch; db_dct reads it back and writes librosa's layout.
+    bool own_scr = false;
+    if (!d_melscr) {
+        CK(cudaMallocAsync((void**)&d_melscr, (size_t)B * T * plan->p.n_mels * 4, st));
+        own_scr = true;
+    }
+    rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_melscr, d_stats, d_status, d_clipmax, nullptr, st,
+                    cand, cand_count, cand_cap, 1);
     if (rc != HLMC_OK) return rc;
     if (plan->timing) CK(cudaEventRecord(ev3[1], st));
     DbArgs d{};
-    d.mel = d_logmel; d.mfcc = d_mfcc; d.clipmax = reinterpret_cast<const unsigned int*>(d_clipmax);
+    d.mel = d_logmel; d.mel_in = d_melscr; d.mfcc = d_mfcc; d.clipmax = reinterpret_cast<const unsigned int*>(d_clipmax);
     d.dct_t = plan->d_dct_t; d.B = (int)B; d.n_mels = plan->p.n_mels; d.n_mfcc = plan->p.n_mfcc;
     d.ncp = plan->ncp; d.T = (int)T; d.ref_mode = plan->p.ref_mode; d.ref_value = plan->p.ref_value;
     d.amin = plan->p.amin; d.top_db = plan->p.top_db;
@@ -555,6 +571,7 @@ int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int6
         CK(cudaEventRecord(ev3[2], st));
         for (auto& e : ev3) plan->ev.push_back(e);
     }
+    if (own_scr) CK(cudaFreeAsync(d_melscr, st));
     if (d_chroma) {
         CK(launch_tuning(cand, cand_count, (int)T, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
         FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
@@ -564,11 +581,19 @@ int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int6
     return HLMC_OK;
 }
 
+int hlmc_extract_device_ex(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                           float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
+                           float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
+                           int64_t work_bytes, void* stream) {
+    return extract_device_impl(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax,
+                               d_chroma, d_tuning, d_work, work_bytes, stream, nullptr);
+}
+
 int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
                         float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
                         float* d_clipmax, void* stream) {
-    return hlmc_extract_device_ex(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax,
-                                  nullptr, nullptr, nullptr, 0, stream);
+    return extract_device_impl(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax,
+                               nullptr, nullptr, nullptr, 0, stream, nullptr);
 }
 
 int hlmc_plan_set_timing(hlmc_plan* plan, int enable) {
@@ -669,7 +694,7 @@ static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, 
     for (auto& s : pl->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     pl->slots.assign(n_streams, HostPipeSlot());
@@ -679,6 +704,7 @@ static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, 
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CK(cudaMalloc((void**)&s.d_wave, (size_t)chunk * dp * 4));
         CK(cudaMalloc((void**)&s.d_logmel, (size_t)chunk * nm * T * 4));
+        CK(cudaMalloc((void**)&s.d_melscr, (size_t)chunk * nm * T * 4));
         if (nc > 0) CK(cudaMalloc((void**)&s.d_mfcc, (size_t)chunk * nc * T * 4));
         CK(cudaMalloc((void**)&s.d_stats, (size_t)chunk * 5 * T * 4));
         CK(cudaMalloc((void**)&s.d_pooled, (size_t)chunk * (2 * nm + 2 * nc + 10) * 4));
@@ -750,8 +776,9 @@ int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format,
                                      (size_t)c, s.stream));
         }
         plan->last_h2d += c * n_valid * (int64_t)esz;
-        rc = hlmc_extract_device(plan, s.d_wave, c, n, dp, s.d_logmel, want_mfcc ? s.d_mfcc : nullptr,
-                                 s.d_stats, s.d_status, s.d_clipmax, s.stream);
+        rc = extract_device_impl(plan, s.d_wave, c, n, dp, s.d_logmel, want_mfcc ? s.d_mfcc : nullptr,
+                                 s.d_stats, s.d_status, s.d_clipmax, nullptr, nullptr, nullptr, 0, s.stream,
+                                 s.d_melscr);
         if (rc != HLMC_OK) return rc;
         if (h_pooled) {
             CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, nullptr, c, nm, nc, (int)T,

@@ -32,7 +32,8 @@ struct FrameArgs {
     float binhz;            // sr / n_fft
     float roll_percent;
     float zcr_thr;
-    float* mel_out;         // (B, n_mels, T) mel power; may be NULL (stats only)
+    float* mel_out;         // mel power, (B, n_mels, T) or -- mel_frame_major -- (B, T, n_mels); may be NULL
+    int mel_frame_major;    // 1: scratch layout for db_dct (coalesced full-sector stores)
     float* stats;           // (B, 5, T) or NULL
     int* status;            // (B) or NULL
     unsigned int* clipmax;  // (B) float bits, max of mel power; or NULL
@@ -66,7 +67,8 @@ struct GenericTables {
 };
 
 struct DbArgs {
-    float* mel;             // in: mel power, out: power_to_db   (B, n_mels, T)
+    float* mel;             // out: power_to_db (B, n_mels, T); also the mel-power input when mel_in == NULL
+    const float* mel_in;    // mel power in frame-major scratch (B, T, n_mels), or NULL
     float* mfcc;            // (B, n_mfcc, T) or NULL
     const unsigned int* clipmax;
     const float* dct_t;     // (n_mels, ncp) transposed, zero padded DCT matrix

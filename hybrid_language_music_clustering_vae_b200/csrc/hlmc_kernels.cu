@@ -331,12 +331,14 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     }
     __syncthreads();
 
-    // ---- this warp's contiguous run of frames
+    // ---- frame assignment: the CTA owns a contiguous run of (clip, frame) pairs and its NW warps
+    //      take them round-robin, so at any moment one SM works on NW neighbouring frames of one
+    //      clip (their 75 %-overlapping samples are hot in L2) and the whole GPU on ~148 clips
     const long long total = (long long)a.B * a.T;
-    const long long nwarps = (long long)gridDim.x * NW;
-    const long long per = (total + nwarps - 1) / nwarps;
-    const long long g0 = ((long long)blockIdx.x * NW + warp) * per;
-    const long long g1 = (g0 + per < total) ? g0 + per : total;
+    const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
+    const long long c0 = (long long)blockIdx.x * per_cta;
+    const long long g1 = (c0 + per_cta < total) ? c0 + per_cta : total;
+    const long long g0 = c0 + warp;
     if (g0 >= g1) return;
     int b = (int)(g0 / a.T);
     int t = (int)(g0 - (long long)b * a.T);
@@ -351,7 +353,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     w.zhi_base = 17 * (63 - lane) + 16;          // read:  k = 1024-16*lane-i (i>=1) -> zhi_base - i
     w.zhi0 = (lane == 0) ? 0 : 17 * (64 - lane); // read:  k = (1024-16*lane) mod 1024
 
-    for (long long g = g0; g < g1; ++g) {
+    for (long long g = g0; g < g1; g += NW) {
         const float* clip = a.wave + (long long)b * a.pitch;
         float vr[64], vi[64];
         float p512, s512, ss, m0l, m1l, m0h, m1h;
@@ -492,7 +494,9 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         //      start offsets were shifted on the host so that the 32 lanes hit 32 banks
         if (a.mel_out != nullptr) {
             float wmax = 0.0f;
-            float* outb = a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+            const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
+            float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
+                                            : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
             for (int g = 0; g < ft.n_groups; ++g) {
                 const int n4 = s_meta[g];
                 const float4* wp = reinterpret_cast<const float4*>(s_melw + s_meta[kMaxMelGroups + g]) + lane;
@@ -520,7 +524,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 a0 += a2; a1 += a3;
                 const float acc = a0 + a1;
                 const int m = 32 * g + lane;
-                if (m < a.n_mels) outb[(size_t)m * a.T] = acc;
+                if (m < a.n_mels) outb[(size_t)m * mstride] = acc;
                 wmax = fmaxf(wmax, acc);
             }
             clip_max = fmaxf(clip_max, wmax);
@@ -538,13 +542,14 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             if (a.status != nullptr && !(fabsf(ss) <= 3.0e38f)) atomicOr(a.status + b, 1);
         }
         // ---- next frame; flush the running mel maximum when the clip (or this warp's run) ends
-        const bool last = (t == a.T - 1) || (g + 1 == g1);
+        const bool last = (t + NW >= a.T) || (g + NW >= g1);
         if (last && a.clipmax != nullptr && a.mel_out != nullptr) {
             const float m = warp_max(clip_max);
             if (lane == 0) atomicMax(reinterpret_cast<int*>(a.clipmax) + b, __float_as_int(m));
             clip_max = 0.0f;
         }
-        if (++t == a.T) { t = 0; ++b; }
+        t += NW;
+        while (t >= a.T) { t -= a.T; ++b; }
         __syncwarp();                       // scratch reads are done before the next frame lands
     }
 }
@@ -941,7 +946,8 @@ frames_generic(const FrameArgs a, const GenericTables gt, int logM) {
                 const float p = Pb[lo + i];
                 acc = fmaf(w[i], a.use_mag ? sqrtf(p) : p, acc);
             }
-            a.mel_out[((size_t)b * a.n_mels + m) * a.T + t] = acc;
+            if (a.mel_frame_major) a.mel_out[((size_t)b * a.T + t) * a.n_mels + m] = acc;
+            else a.mel_out[((size_t)b * a.n_mels + m) * a.T + t] = acc;
             wmax = fmaxf(wmax, acc);
         }
         wmax = warp_max(wmax);
@@ -994,11 +1000,20 @@ __global__ void __launch_bounds__(128) db_dct(const DbArgs a) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.0f;
     float* col = a.mel + (size_t)b * a.n_mels * a.T + t;
+    const float* row = a.mel_in ? a.mel_in + ((size_t)b * a.T + t) * a.n_mels : nullptr;
+    const bool vec = (row != nullptr) && ((a.n_mels & 3) == 0);
     constexpr int MB = 8;                       // mel rows fetched per batch: 8 independent loads in flight
     for (int m0 = 0; m0 < a.n_mels; m0 += MB) {
         float pv[MB];
+        if (vec && m0 + MB <= a.n_mels) {       // frame-major scratch: two 16-byte loads
+            const float4 u = __ldg(reinterpret_cast<const float4*>(row + m0));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + m0 + 4));
+            pv[0] = u.x; pv[1] = u.y; pv[2] = u.z; pv[3] = u.w; pv[4] = v.x; pv[5] = v.y; pv[6] = v.z; pv[7] = v.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < MB; ++j) pv[j] = (m0 + j < a.n_mels) ? col[(size_t)(m0 + j) * a.T] : 0.0f;
+            for (int j = 0; j < MB; ++j)
+                pv[j] = (m0 + j < a.n_mels) ? (row ? row[m0 + j] : col[(size_t)(m0 + j) * a.T]) : 0.0f;
+        }
 #pragma unroll
         for (int j = 0; j < MB; ++j) {
             const int m = m0 + j;
