@@ -21,6 +21,7 @@ EXPORTS = (
     "hlmc_extract_host", "hlmc_last_transfer_bytes", "hlmc_measure_fp32_peak",
     "hlmc_plan_set_timing", "hlmc_plan_read_timing", "hlmc_extract_host_ex",
     "hlmc_chroma_workspace_bytes", "hlmc_extract_device_ex", "hlmc_pool_device_ex",
+    "hlmc_extract_host_io",
 )
 
 HLMC_OK, HLMC_ERR_PARAM, HLMC_ERR_UNSUPPORTED, HLMC_ERR_CUDA, HLMC_ERR_NOMEM = 0, -1, -2, -3, -4
@@ -38,6 +39,18 @@ class HlmcParams(C.Structure):
         ("n_mfcc", C.c_int32), ("lifter", C.c_float), ("ref_mode", C.c_int32), ("ref_value", C.c_float),
         ("amin", C.c_float), ("top_db", C.c_float), ("roll_percent", C.c_float),
         ("zcr_threshold", C.c_float),
+    ]
+
+
+class HlmcHostIo(C.Structure):
+    """Mirror of ``struct hlmc_host_io``."""
+
+    _fields_ = [
+        ("wave", C.c_void_p), ("sample_format", C.c_int32), ("B", C.c_int64), ("n_valid", C.c_int64),
+        ("pitch", C.c_int64), ("n_total", C.c_int64), ("logmel", C.c_void_p), ("mfcc", C.c_void_p),
+        ("stats", C.c_void_p), ("chroma", C.c_void_p), ("tuning", C.c_void_p), ("pooled", C.c_void_p),
+        ("status", C.c_void_p), ("pooled_with_chroma", C.c_int32), ("chunk_clips", C.c_int64),
+        ("n_streams", C.c_int32),
     ]
 
 
@@ -77,6 +90,7 @@ def _load():
     lib.hlmc_chroma_workspace_bytes.restype = i64
     lib.hlmc_extract_device_ex.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.hlmc_pool_device_ex.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp]
+    lib.hlmc_extract_host_io.argtypes = [vp, C.POINTER(HlmcHostIo)]
     lib.hlmc_last_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.hlmc_last_transfer_bytes.restype = None
     lib.hlmc_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

@@ -15,7 +15,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import HlmcParams, lib
+from ._lib import HlmcHostIo, HlmcParams, lib
 
 STAT_NAMES = ("spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "zcr", "rms")
 
@@ -287,7 +287,7 @@ class FeatureExtractor:
 
     # -- host path (the reference-facing call) ---------------------------------
     def extract_host(self, waves, *, logmel=True, mfcc=True, stats=True, status=True, pooled=False,
-                     chunk_clips=0, n_streams=3, out=None, pad_to=None):
+                     chroma=False, chunk_clips=0, n_streams=3, out=None, pad_to=None):
         """(B, n) host float32 -- or int16 PCM -- (numpy or CPU torch, ideally pinned) -> dict of numpy arrays.
 
         H2D copies, kernels and D2H copies are overlapped inside the C library.  int16 input is
@@ -339,13 +339,17 @@ class FeatureExtractor:
         mf = buf("mfcc", (B, self.n_mfcc, T)) if mfcc else None
         st = buf("stats", (B, 5, T)) if stats else None
         sta = buf("status", (B,), np.int32) if status else None
-        po = buf("pooled", (B, self.pooled_width(self.n_mfcc > 0))) if pooled else None
-        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        po = buf("pooled", (B, self.pooled_width(self.n_mfcc > 0, bool(chroma)))) if pooled else None
+        ch = buf("chroma", (B, 12, T)) if (chroma and chroma != "pooled") else None     # "pooled": columns only
+        tu = buf("tuning", (B,)) if (chroma and chroma != "pooled") else None
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        io = HlmcHostIo(wave=ptr(waves), sample_format=1 if pcm16 else 0, B=B, n_valid=n,
+                        pitch=n if B == 1 else waves.strides[0] // esz, n_total=n_total, logmel=ptr(lm),
+                        mfcc=ptr(mf), stats=ptr(st), chroma=ptr(ch), tuning=ptr(tu), pooled=ptr(po),
+                        status=ptr(sta), pooled_with_chroma=int(bool(chroma)), chunk_clips=int(chunk_clips),
+                        n_streams=int(n_streams))
         with self._lock:
-            pitch = n if B == 1 else waves.strides[0] // esz
-            _check(lib.hlmc_extract_host_ex(self._plan, ptr(waves), 1 if pcm16 else 0, B, n, pitch, n_total,
-                                            ptr(lm), ptr(mf), ptr(st), ptr(sta), ptr(po), int(chunk_clips),
-                                            int(n_streams)))
+            _check(lib.hlmc_extract_host_io(self._plan, C.byref(io)))
         del tensor_in
         return out
 

@@ -37,6 +37,7 @@ struct HostPipeSlot {
     int32_t* d_status = nullptr;
     int16_t* d_raw = nullptr; size_t raw_elems = 0;     // PCM16 staging (hlmc_extract_host_ex)
     float* d_melscr = nullptr;                           // frame-major mel-power scratch
+    float* d_chroma = nullptr; float* d_tuning = nullptr; void* d_cwork = nullptr; size_t chroma_ws = 0;
 };
 
 struct hlmc_plan {
@@ -234,7 +235,7 @@ void hlmc_plan_destroy(hlmc_plan* plan) {
     for (auto& s : plan->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr); cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(plan->d_fast); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
@@ -694,7 +695,7 @@ static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, 
     for (auto& s : pl->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr); cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     pl->slots.assign(n_streams, HostPipeSlot());
@@ -715,22 +716,29 @@ static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, 
     return HLMC_OK;
 }
 
-int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format, int64_t B,
-                         int64_t n_valid, int64_t h_pitch, int64_t n_total, float* h_logmel, float* h_mfcc,
-                         float* h_stats, int32_t* h_status, float* h_pooled, int64_t chunk_clips,
-                         int n_streams) {
+int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
+    if (!plan || !io) return fail(HLMC_ERR_PARAM, "null argument");
+    const int sample_format = io->sample_format;
+    const int64_t B = io->B, n_valid = io->n_valid, h_pitch = io->pitch;
+    const int64_t n_total = io->n_total > 0 ? io->n_total : io->n_valid;
+    int64_t chunk_clips = io->chunk_clips;
+    int n_streams = io->n_streams;
     if (sample_format != HLMC_SAMPLES_F32 && sample_format != HLMC_SAMPLES_PCM16)
         return fail(HLMC_ERR_PARAM, "unknown sample_format");
     if (n_total < n_valid) return fail(HLMC_ERR_PARAM, "n_total < n_valid");
     int64_t T;
     const int64_t n = n_total;
-    if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
     if (h_pitch < n_valid) return fail(HLMC_ERR_PARAM, "pitch < n");
-    int rc = check_batch(plan, h_wave, B, n, n, &T);
+    int rc = check_batch(plan, io->wave, B, n, n, &T);
     if (rc != HLMC_OK) return rc;
     plan->last_h2d = plan->last_d2h = 0;
     if (B == 0) return HLMC_OK;
-    if (h_mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
+    if (io->mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
+    const bool want_chroma = io->chroma || io->tuning || (io->pooled && io->pooled_with_chroma);
+    if (want_chroma) {
+        rc = ensure_chroma_tables(plan);
+        if (rc != HLMC_OK) return rc;
+    }
     CK(cudaSetDevice(plan->device));
     if (n_streams <= 0) n_streams = 3;
     if (n_streams > 8) n_streams = 8;
@@ -745,24 +753,40 @@ int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format,
     const int64_t rp = (n_valid + 7) & ~int64_t(7);           // PCM16 staging pitch (16-B rows)
     const bool pcm = (sample_format == HLMC_SAMPLES_PCM16);
     const size_t esz = pcm ? 2 : 4;
-    if (pcm) {
-        for (auto& s : plan->slots) {
-            if (s.raw_elems < (size_t)(plan->slot_chunk * rp)) {
-                cudaFree(s.d_raw);
-                s.d_raw = nullptr;
-                CK(cudaMalloc((void**)&s.d_raw, (size_t)plan->slot_chunk * rp * 2));
-                s.raw_elems = (size_t)plan->slot_chunk * rp;
+    int64_t chroma_ws = 0;
+    for (auto& s : plan->slots) {
+        if (pcm && s.raw_elems < (size_t)(plan->slot_chunk * rp)) {
+            cudaFree(s.d_raw);
+            s.d_raw = nullptr;
+            CK(cudaMalloc((void**)&s.d_raw, (size_t)plan->slot_chunk * rp * 2));
+            s.raw_elems = (size_t)plan->slot_chunk * rp;
+        }
+        if (want_chroma) {
+            chroma_ws = hlmc_chroma_workspace_bytes(plan, plan->slot_chunk, n);
+            if (chroma_ws < 0) return (int)chroma_ws;
+            if (s.chroma_ws < (size_t)chroma_ws) {
+                cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork);
+                s.d_chroma = nullptr; s.d_tuning = nullptr; s.d_cwork = nullptr;
+                CK(cudaMalloc((void**)&s.d_chroma, (size_t)plan->slot_chunk * kChroma * T * 4));
+                CK(cudaMalloc((void**)&s.d_tuning, (size_t)plan->slot_chunk * 4));
+                CK(cudaMalloc((void**)&s.d_cwork, (size_t)chroma_ws));
+                CK(cudaFree(s.d_pooled));
+                s.d_pooled = nullptr;
+                CK(cudaMalloc((void**)&s.d_pooled, (size_t)plan->slot_chunk *
+                                                       (2 * plan->p.n_mels + 2 * plan->p.n_mfcc + 10 + 2 * kChroma) * 4));
+                s.chroma_ws = (size_t)chroma_ws;
             }
         }
     }
     const int nm = plan->p.n_mels, nc = plan->p.n_mfcc;
-    const bool want_mfcc = (h_mfcc != nullptr) || (h_pooled != nullptr && nc > 0);
-    const int pooled_w = 2 * nm + 2 * (want_mfcc ? nc : 0) + 10;
+    const bool want_mfcc = (io->mfcc != nullptr) || (io->pooled != nullptr && nc > 0);
+    const bool pool_chroma = io->pooled && io->pooled_with_chroma;
+    const int pooled_w = 2 * nm + 2 * (want_mfcc ? nc : 0) + 10 + (pool_chroma ? 2 * kChroma : 0);
     int64_t done = 0;
     for (int64_t i = 0; done < B; ++i) {
         HostPipeSlot& s = plan->slots[i % n_streams];
         const int64_t c = (B - done < chunk_clips) ? (B - done) : chunk_clips;
-        const char* src = static_cast<const char*>(h_wave) + (size_t)done * h_pitch * esz;
+        const char* src = static_cast<const char*>(io->wave) + (size_t)done * h_pitch * esz;
         if (pcm) {
             // [R] librosa.load on a PCM16 file: float32 = int16 / 32768; then the scripts' zero pad
             CK(cudaMemcpy2DAsync(s.d_raw, (size_t)rp * 2, src, (size_t)h_pitch * 2, (size_t)n_valid * 2,
@@ -777,39 +801,41 @@ int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format,
         }
         plan->last_h2d += c * n_valid * (int64_t)esz;
         rc = extract_device_impl(plan, s.d_wave, c, n, dp, s.d_logmel, want_mfcc ? s.d_mfcc : nullptr,
-                                 s.d_stats, s.d_status, s.d_clipmax, nullptr, nullptr, nullptr, 0, s.stream,
-                                 s.d_melscr);
+                                 s.d_stats, s.d_status, s.d_clipmax, want_chroma ? s.d_chroma : nullptr,
+                                 want_chroma ? s.d_tuning : nullptr, want_chroma ? s.d_cwork : nullptr,
+                                 chroma_ws, s.stream, s.d_melscr);
         if (rc != HLMC_OK) return rc;
-        if (h_pooled) {
-            CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, nullptr, c, nm, nc, (int)T,
-                           s.d_pooled, s.stream));
-            CK(cudaMemcpyAsync(h_pooled + done * pooled_w, s.d_pooled, (size_t)c * pooled_w * 4,
-                               cudaMemcpyDeviceToHost, s.stream));
-            plan->last_d2h += c * pooled_w * 4;
+        auto d2h = [&](void* dst, const void* srcd, size_t bytes) -> cudaError_t {
+            plan->last_d2h += (int64_t)bytes;
+            return cudaMemcpyAsync(dst, srcd, bytes, cudaMemcpyDeviceToHost, s.stream);
+        };
+        if (io->pooled) {
+            CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, pool_chroma ? s.d_chroma : nullptr,
+                           c, nm, nc, (int)T, s.d_pooled, s.stream));
+            CK(d2h(io->pooled + done * pooled_w, s.d_pooled, (size_t)c * pooled_w * 4));
         }
-        if (h_logmel) {
-            CK(cudaMemcpyAsync(h_logmel + done * nm * T, s.d_logmel, (size_t)c * nm * T * 4,
-                               cudaMemcpyDeviceToHost, s.stream));
-            plan->last_d2h += c * nm * T * 4;
-        }
-        if (h_mfcc) {
-            CK(cudaMemcpyAsync(h_mfcc + done * nc * T, s.d_mfcc, (size_t)c * nc * T * 4,
-                               cudaMemcpyDeviceToHost, s.stream));
-            plan->last_d2h += c * nc * T * 4;
-        }
-        if (h_stats) {
-            CK(cudaMemcpyAsync(h_stats + done * 5 * T, s.d_stats, (size_t)c * 5 * T * 4,
-                               cudaMemcpyDeviceToHost, s.stream));
-            plan->last_d2h += c * 5 * T * 4;
-        }
-        if (h_status) {
-            CK(cudaMemcpyAsync(h_status + done, s.d_status, (size_t)c * 4, cudaMemcpyDeviceToHost, s.stream));
-            plan->last_d2h += c * 4;
-        }
+        if (io->logmel) CK(d2h(io->logmel + done * nm * T, s.d_logmel, (size_t)c * nm * T * 4));
+        if (io->mfcc) CK(d2h(io->mfcc + done * nc * T, s.d_mfcc, (size_t)c * nc * T * 4));
+        if (io->stats) CK(d2h(io->stats + done * 5 * T, s.d_stats, (size_t)c * 5 * T * 4));
+        if (io->chroma) CK(d2h(io->chroma + done * kChroma * T, s.d_chroma, (size_t)c * kChroma * T * 4));
+        if (io->tuning) CK(d2h(io->tuning + done, s.d_tuning, (size_t)c * 4));
+        if (io->status) CK(d2h(io->status + done, s.d_status, (size_t)c * 4));
         done += c;
     }
     for (auto& s : plan->slots) CK(cudaStreamSynchronize(s.stream));
     return HLMC_OK;
+}
+
+int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format, int64_t B,
+                         int64_t n_valid, int64_t h_pitch, int64_t n_total, float* h_logmel, float* h_mfcc,
+                         float* h_stats, int32_t* h_status, float* h_pooled, int64_t chunk_clips,
+                         int n_streams) {
+    hlmc_host_io io;
+    memset(&io, 0, sizeof(io));
+    io.wave = h_wave; io.sample_format = sample_format; io.B = B; io.n_valid = n_valid; io.pitch = h_pitch;
+    io.n_total = n_total; io.logmel = h_logmel; io.mfcc = h_mfcc; io.stats = h_stats; io.status = h_status;
+    io.pooled = h_pooled; io.chunk_clips = chunk_clips; io.n_streams = n_streams;
+    return hlmc_extract_host_io(plan, &io);
 }
 
 int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n, int64_t h_pitch,

@@ -123,8 +123,9 @@ def extract_all_features_batch(waves, sr=22050, cfg=BASIC_CONFIG, chroma="device
     ex = _basic_extractor(dict(cfg, sample_rate=sr), device=device)
     waves = np.asarray(waves)
     if isinstance(chroma, str) and chroma == "device":
-        pooled, status = _pooled_on_device(ex, waves, True, device, chunk_clips)
-        feats = pooled.astype(np.float64)
+        r = ex.extract_host(waves, logmel=False, mfcc=False, stats=False, pooled=True, chroma="pooled")
+        status = r["status"]
+        feats = r["pooled"].astype(np.float64)
     else:
         r = ex.extract_host(waves, logmel=False, mfcc=False, stats=False, pooled=True)
         status = r["status"]

@@ -216,6 +216,26 @@ int hlmc_extract_host_ex(hlmc_plan *plan, const void *h_wave, int sample_format,
                          float *h_mfcc, float *h_stats, int32_t *h_status, float *h_pooled,
                          int64_t chunk_clips, int n_streams);
 
+/* The general host entry point: everything above plus chroma_stft, as one POD request.
+ * Any output pointer may be NULL.  pooled_with_chroma != 0 appends [chroma mean | chroma std]
+ * to the pooled rows (the scripts' full 370 / 290 columns).                              */
+typedef struct hlmc_host_io {
+    const void *wave;          /* (B, pitch) float32 or int16                             */
+    int32_t     sample_format; /* HLMC_SAMPLES_*                                          */
+    int64_t     B, n_valid, pitch, n_total;   /* n_total <= 0 means n_valid               */
+    float      *logmel;        /* (B, n_mels, T)                                          */
+    float      *mfcc;          /* (B, n_mfcc, T)                                          */
+    float      *stats;         /* (B, 5, T)                                               */
+    float      *chroma;        /* (B, 12, T)                                              */
+    float      *tuning;        /* (B)                                                     */
+    float      *pooled;        /* (B, 2*n_mels + 2*n_mfcc + 10 [+ 24])                    */
+    int32_t    *status;        /* (B)                                                     */
+    int32_t     pooled_with_chroma;
+    int64_t     chunk_clips;   /* <= 0: chosen by the library                             */
+    int32_t     n_streams;     /* <= 0: 3                                                 */
+} hlmc_host_io;
+int hlmc_extract_host_io(hlmc_plan *plan, const hlmc_host_io *io);
+
 /* Bytes moved by the last hlmc_extract_host call on this plan.               */
 void hlmc_last_transfer_bytes(const hlmc_plan *plan, int64_t *h2d, int64_t *d2h);
 

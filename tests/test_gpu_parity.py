@@ -393,6 +393,11 @@ def test_chroma_stft_and_tuning_on_device(built):
         # pooled chroma columns = mean / std over frames
         po = out["pooled"].cpu().numpy()
         assert np.abs(po[:, 346:358] - ch.mean(-1)).max() <= 1e-5 and np.abs(po[:, 358:370] - ch.std(-1)).max() <= 1e-5
+    # the host pipeline produces the same chroma (chunked, overlapped copies)
+    hp = ex.extract_host(y, chroma=True, pooled=True, chunk_clips=7)
+    assert np.array_equal(hp["chroma"], ch) and np.array_equal(hp["tuning"], tu) and np.array_equal(hp["pooled"], po)
+    hp2 = ex.extract_host(y, logmel=False, mfcc=False, stats=False, pooled=True, chroma="pooled")
+    assert "chroma" not in hp2 and np.array_equal(hp2["pooled"], po)
     c1 = hl.feature.chroma_stft(y=y[3], sr=SR, n_fft=2048, hop_length=512)
     assert c1.shape == (12, 130) and np.array_equal(c1, ch[3])
     with pytest.raises(hl.UnsupportedError):
