@@ -344,6 +344,12 @@ def main():
     step_bytes = B * algorithmic_bytes_per_clip(n, T)
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
     traffic = load_traffic()
+    ncu_pipe = None
+    try:      # FP32-pipe / issue / shared-memory utilisation of the same kernel from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "frames_fast_pipes.json")) as f:
+            ncu_pipe = json.load(f)
+    except Exception:
+        pass
     fp32_peak = hl.measure_fp32_peak(local_rank)
     flops_step = B * T * algorithmic_flops_per_frame()
     roofline = {
@@ -358,7 +364,8 @@ def main():
         "fp32": {"achieved_tflops": flops_step / (ms / args.steps * 1e-3) / 1e12,
                  "peak_tflops": fp32_peak, "peak_source": "FMA micro-benchmark run in this process",
                  "frac": flops_step / (ms / args.steps * 1e-3) / 1e12 / fp32_peak,
-                 "algorithmic_flops_per_frame": algorithmic_flops_per_frame()},
+                 "algorithmic_flops_per_frame": algorithmic_flops_per_frame(),
+                 "ncu": ncu_pipe},
     }
 
     cpu = None

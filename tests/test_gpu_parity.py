@@ -402,3 +402,25 @@ def test_chroma_stft_and_tuning_on_device(built):
     assert c1.shape == (12, 130) and np.array_equal(c1, ch[3])
     with pytest.raises(hl.UnsupportedError):
         hl.FeatureExtractor(n_fft=1024).extract_device(torch.zeros(1, 8000, device="cuda"), chroma=True)
+
+
+def test_empty_and_degenerate_batches(built):
+    """Empty batch, empty clip, single sample, single clip: shapes and errors as librosa would give them."""
+    import torch
+
+    hl = built
+    ex = hl.FeatureExtractor(ref=np.max, n_mfcc=40)
+    out = ex.extract_device(torch.zeros((0, 22050), device="cuda"), pooled=True)
+    assert out["logmel"].shape == (0, 128, 44) and out["mfcc"].shape == (0, 40, 44) and out["pooled"].shape == (0, 346)
+    host = ex.extract_host(np.zeros((0, 22050), np.float32))
+    assert host["logmel"].shape == (0, 128, 44) and host["status"].shape == (0,)
+    with pytest.raises(hl.ParameterError):
+        ex.extract_host(np.zeros((3, 0), np.float32))             # librosa: input too short
+    with pytest.raises(hl.ParameterError):
+        hl.FeatureExtractor(center=False).extract_host(np.zeros((2, 1000), np.float32))   # n < n_fft, uncentered
+    one = ex.extract_host(np.full((1, 1), 0.5, np.float32))
+    assert one["logmel"].shape == (1, 128, 1) and one["logmel"].max() == 0.0
+    # a 1-D clip is a batch of one
+    y = hl.synth.synth_batch(1, 5000, seed=2)[0]
+    a = ex.extract_host(y)
+    assert a["logmel"].shape == (1, 128, 10)

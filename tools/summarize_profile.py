@@ -57,6 +57,16 @@ for k in summary:
             json.dump({"source": f"profiles/{tag}_ncu_summary.json (ncu --set full, one launch)",
                        "clips_in_capture": clips, "dram_bytes_read": rd, "dram_bytes_write": wr,
                        "dram_bytes_per_launch": rd + wr, "dram_bytes_per_clip": (rd + wr) / clips}, f, indent=1)
+        with open(os.path.join(out_dir, "frames_fast_pipes.json"), "w") as f:
+            json.dump({"source": f"profiles/{tag}_ncu_summary.json (ncu --set full, one launch, {clips} clips)",
+                       "fma_pipe_pct": k.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                       "alu_pipe_pct": k.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                       "lsu_pipe_pct": k.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                       "issue_slots_busy_pct": k.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                       "shared_mem_pipe_pct": k.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                       "dram_pct": k.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                       "registers_per_thread": k.get("launch__registers_per_thread"),
+                       "warp_instructions_per_frame": k.get("smsp__inst_executed.sum", 0) / (clips * 130.0)}, f, indent=1)
         break
 
 # launch list: keep our kernels' rows
@@ -106,4 +116,12 @@ for c in pick[:1]:
                 mix[op] = mix.get(op, 0) + 1
 with open(os.path.join(out_dir, f"{tag}_sass_mix_frames_fast.json"), "w") as f:
     json.dump(dict(sorted(mix.items(), key=lambda kv: -kv[1])), f, indent=1)
+# the Blackwell / TMA evidence lines of the frames kernel
+ev = []
+for line in pick[0].splitlines() if pick else []:
+    if any(op in line for op in ("UBLKCP", "SYNCS", "MUFU.SQRT", "FENCE.VIEW.ASYNC", "UTMA")):
+        ev.append(line.rstrip())
+with open(os.path.join(out_dir, f"{tag}_sass_evidence.txt"), "w") as f:
+    f.write("# frames_fast_2048<16,false>: TMA bulk copy (UBLKCP), mbarrier (SYNCS), async-proxy fence, MUFU lines\n")
+    f.write("\n".join(ev) + "\n")
 print("wrote profiles/", tag)
