@@ -21,7 +21,7 @@ EXPORTS = (
     "hlmc_extract_host", "hlmc_last_transfer_bytes", "hlmc_measure_fp32_peak",
     "hlmc_plan_set_timing", "hlmc_plan_read_timing", "hlmc_extract_host_ex",
     "hlmc_chroma_workspace_bytes", "hlmc_extract_device_ex", "hlmc_pool_device_ex",
-    "hlmc_extract_host_io",
+    "hlmc_extract_host_io", "hlmc_column_stats_device", "hlmc_standardize_device",
 )
 
 HLMC_OK, HLMC_ERR_PARAM, HLMC_ERR_UNSUPPORTED, HLMC_ERR_CUDA, HLMC_ERR_NOMEM = 0, -1, -2, -3, -4
@@ -91,6 +91,8 @@ def _load():
     lib.hlmc_extract_device_ex.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.hlmc_pool_device_ex.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp]
     lib.hlmc_extract_host_io.argtypes = [vp, C.POINTER(HlmcHostIo)]
+    lib.hlmc_column_stats_device.argtypes = [vp, i64, i64, vp, vp, C.c_int, vp]
+    lib.hlmc_standardize_device.argtypes = [vp, vp, i64, i64, vp, vp, C.c_int, vp]
     lib.hlmc_last_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.hlmc_last_transfer_bytes.restype = None
     lib.hlmc_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

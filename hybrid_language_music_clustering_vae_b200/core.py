@@ -66,7 +66,7 @@ def _ref_to_mode(ref):
 
 def _row_pitch(w):
     """Row pitch in elements; a single-row tensor may carry an arbitrary stride(0)."""
-    return w.shape[1] if w.shape[0] == 1 else w.stride(0)
+    return w.shape[1] if w.shape[0] <= 1 else w.stride(0)
 
 
 class FeatureExtractor:
@@ -344,7 +344,7 @@ class FeatureExtractor:
         tu = buf("tuning", (B,)) if (chroma and chroma != "pooled") else None
         ptr = lambda a: a.ctypes.data if a is not None else None
         io = HlmcHostIo(wave=ptr(waves), sample_format=1 if pcm16 else 0, B=B, n_valid=n,
-                        pitch=n if B == 1 else waves.strides[0] // esz, n_total=n_total, logmel=ptr(lm),
+                        pitch=n if B <= 1 else waves.strides[0] // esz, n_total=n_total, logmel=ptr(lm),
                         mfcc=ptr(mf), stats=ptr(st), chroma=ptr(ch), tuning=ptr(tu), pooled=ptr(po),
                         status=ptr(sta), pooled_with_chroma=int(bool(chroma)), chunk_clips=int(chunk_clips),
                         n_streams=int(n_streams))

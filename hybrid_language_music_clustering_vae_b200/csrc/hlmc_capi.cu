@@ -663,8 +663,9 @@ int hlmc_power_to_db_device(const float* d_in, float* d_out, int64_t B, int64_t 
 
 int hlmc_pool_device_ex(hlmc_plan* plan, const float* d_logmel, const float* d_mfcc, const float* d_stats,
                         const float* d_chroma, int64_t B, int64_t T, float* d_pooled, void* stream) {
-    if (!plan || !d_logmel || !d_stats || !d_pooled) return fail(HLMC_ERR_PARAM, "null argument");
+    if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
     if (B <= 0 || T <= 0) return HLMC_OK;
+    if (!d_logmel || !d_stats || !d_pooled) return fail(HLMC_ERR_PARAM, "null argument");
     CK(cudaSetDevice(plan->device));
     CK(launch_pool(d_logmel, d_mfcc, d_stats, d_chroma, B, plan->p.n_mels, plan->p.n_mfcc, (int)T, d_pooled,
                    static_cast<cudaStream_t>(stream)));
@@ -843,6 +844,24 @@ int hlmc_extract_host(hlmc_plan* plan, const float* h_wave, int64_t B, int64_t n
                       int64_t chunk_clips, int n_streams) {
     return hlmc_extract_host_ex(plan, h_wave, HLMC_SAMPLES_F32, B, n, h_pitch, n, h_logmel, h_mfcc, h_stats,
                                 h_status, h_pooled, chunk_clips, n_streams);
+}
+
+int hlmc_column_stats_device(const float* d_x, int64_t N, int64_t D, double* d_mean, double* d_m2,
+                             int device, void* stream) {
+    if (!d_x || !d_mean || !d_m2) return fail(HLMC_ERR_PARAM, "null argument");
+    if (N < 0 || D < 0) return fail(HLMC_ERR_PARAM, "negative shape");
+    CK(cudaSetDevice(device));
+    CK(launch_colstats(d_x, N, D, d_mean, d_m2, static_cast<cudaStream_t>(stream)));
+    return HLMC_OK;
+}
+
+int hlmc_standardize_device(const float* d_x, float* d_y, int64_t N, int64_t D, const float* d_mean,
+                            const float* d_scale, int device, void* stream) {
+    if (!d_x || !d_y || !d_mean || !d_scale) return fail(HLMC_ERR_PARAM, "null argument");
+    if (N < 0 || D < 0) return fail(HLMC_ERR_PARAM, "negative shape");
+    CK(cudaSetDevice(device));
+    CK(launch_standardize(d_x, d_y, N, D, d_mean, d_scale, static_cast<cudaStream_t>(stream)));
+    return HLMC_OK;
 }
 
 void hlmc_last_transfer_bytes(const hlmc_plan* plan, int64_t* h2d, int64_t* d2h) {

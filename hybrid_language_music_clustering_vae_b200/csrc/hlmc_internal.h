@@ -96,6 +96,10 @@ cudaError_t launch_fix_frames(const float* in, float* out, long long B, int rows
                               cudaStream_t stream);
 cudaError_t launch_pcm16_to_f32(const int16_t* raw, long long raw_pitch, float* out, long long pitch,
                                 long long B, long long n_valid, long long n_total, cudaStream_t stream);
+cudaError_t launch_colstats(const float* x, long long N, long long D, double* mean, double* m2,
+                            cudaStream_t stream);
+cudaError_t launch_standardize(const float* x, float* y, long long N, long long D, const float* mean,
+                               const float* scale, cudaStream_t stream);
 cudaError_t measure_fp32_peak(double* tflops);
 int fast_smem_bytes(const FastTables& ft, int nwarps, int n_fft, int hop, int n_mels);
 int pick_fast_warps(int T);

@@ -1215,6 +1215,53 @@ cudaError_t launch_fix_frames(const float* in, float* out, long long B, int rows
 }
 
 // ---------------------------------------------------------------------------
+// sklearn.preprocessing.StandardScaler on device ([R] src/1_preprocessing_advanced.py:376-382:
+// the (N, 131072) flattened mel images).  Column statistics in float64, two passes like
+// sklearn's _incremental_mean_and_var; one thread per column, rows walked with coalesced reads.
+// ---------------------------------------------------------------------------
+__global__ void colstats_kernel(const float* __restrict__ x, long long N, long long D,
+                                double* __restrict__ mean, double* __restrict__ m2) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    double s = 0.0;
+    for (long long r = 0; r < N; ++r) s += (double)x[r * D + c];
+    const double mu = (N > 0) ? s / (double)N : 0.0;
+    double d1 = 0.0, d2 = 0.0;
+    for (long long r = 0; r < N; ++r) {
+        const double d = (double)x[r * D + c] - mu;
+        d1 += d;
+        d2 = fma(d, d, d2);
+    }
+    mean[c] = mu;
+    m2[c] = (N > 0) ? d2 - d1 * d1 / (double)N : 0.0;      // sum of squared deviations (corrected)
+}
+cudaError_t launch_colstats(const float* x, long long N, long long D, double* mean, double* m2,
+                            cudaStream_t stream) {
+    if (D <= 0) return cudaSuccess;
+    colstats_kernel<<<(unsigned)((D + 127) / 128), 128, 0, stream>>>(x, N, D, mean, m2);
+    g_launches++;
+    return cudaGetLastError();
+}
+__global__ void standardize_kernel(const float* __restrict__ x, float* __restrict__ y, long long total,
+                                   long long D, const float* __restrict__ mean, const float* __restrict__ scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long c = i % D;
+        y[i] = (x[i] - mean[c]) / scale[c];                 // sklearn: X -= mean_; X /= scale_ in X's dtype
+    }
+}
+cudaError_t launch_standardize(const float* x, float* y, long long N, long long D, const float* mean,
+                               const float* scale, cudaStream_t stream) {
+    const long long total = N * D;
+    if (total <= 0) return cudaSuccess;
+    long long grid = (total + 255) / 256;
+    if (grid > 148 * 32) grid = 148 * 32;
+    standardize_kernel<<<(unsigned)grid, 256, 0, stream>>>(x, y, total, D, mean, scale);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Front end of [R] load_audio_file for PCM16 sources: float32 = int16 / 32768 (what
 // librosa.load -> soundfile returns) and the scripts' right zero-pad to `n_total` samples,
 // done on the device so only the valid int16 samples cross PCIe.

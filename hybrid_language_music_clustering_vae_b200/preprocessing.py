@@ -230,16 +230,28 @@ def save_processed_data1(out_dir, features, labels, metadata_df=None, config=BAS
 
 
 def save_processed_data2(out_dir, mel_spectrograms, flat_features, labels, lyrics_embeddings=None,
-                         metadata_df=None, config=ADV_CONFIG):
-    """[R] _advanced.py:376-421: scale the flattened mel images and the 290-vectors, save."""
+                         metadata_df=None, config=ADV_CONFIG, device_scaler=None):
+    """[R] _advanced.py:376-421: scale the flattened mel images and the 290-vectors, save.
+
+    ``device_scaler``: CUDA device ordinal to fit / apply the big (N, 131072) mel StandardScaler on
+    the GPU; None keeps it in sklearn on the host.  Either way ``mel_scaler.pkl`` is
+    a sklearn StandardScaler."""
     from sklearn.impute import SimpleImputer
     from sklearn.preprocessing import StandardScaler
 
     os.makedirs(out_dir, exist_ok=True)
     mel = np.asarray(mel_spectrograms, dtype=np.float32)
     n, h, w = mel.shape
-    mel_scaler = StandardScaler()
-    mel_norm = mel_scaler.fit_transform(mel.reshape(n, -1)).reshape(n, h, w).astype(np.float32)
+    if device_scaler is None:
+        mel_scaler = StandardScaler()
+        mel_norm = mel_scaler.fit_transform(mel.reshape(n, -1)).reshape(n, h, w).astype(np.float32)
+    else:
+        import torch
+        from .scaler import fit_transform_device
+
+        xd = torch.from_numpy(np.ascontiguousarray(mel.reshape(n, -1))).to(torch.device("cuda", device_scaler))
+        yd, mel_scaler = fit_transform_device(xd, inplace=True)
+        mel_norm = yd.cpu().numpy().reshape(n, h, w)
     flat = np.asarray(flat_features, dtype=np.float64)
     flat = np.where(np.isinf(flat), np.nan, flat)
     imputer = SimpleImputer(strategy="mean", keep_empty_features=True)

@@ -239,6 +239,18 @@ int hlmc_extract_host_io(hlmc_plan *plan, const hlmc_host_io *io);
 /* Bytes moved by the last hlmc_extract_host call on this plan.               */
 void hlmc_last_transfer_bytes(const hlmc_plan *plan, int64_t *h2d, int64_t *d2h);
 
+/* sklearn.preprocessing.StandardScaler for the big (N, 131072) mel matrix
+ * ([R] src/1_preprocessing_advanced.py:376-382), SURVEY.md 8f-4.
+ *   hlmc_column_stats_device: per column, float64 mean and corrected sum of squared deviations
+ *     (var = m2 / N), computed like sklearn's _incremental_mean_and_var; per-rank results combine
+ *     across GPUs with Chan's formula (the one collective of the whole path, done by the caller);
+ *   hlmc_standardize_device: y = (x - mean) / scale in float32, as StandardScaler.transform does
+ *     for float32 input.  In place when d_y == d_x.                                           */
+int hlmc_column_stats_device(const float *d_x, int64_t N, int64_t D, double *d_mean, double *d_m2,
+                             int device, void *stream);
+int hlmc_standardize_device(const float *d_x, float *d_y, int64_t N, int64_t D,
+                            const float *d_mean, const float *d_scale, int device, void *stream);
+
 /* Measurement helper: a dependent-FMA micro-benchmark that returns the
  * achieved FP32 TFLOP/s of the plan's device (the FP32-pipe roofline
  * denominator of SURVEY.md 8(d)); no product path calls it.                  */

@@ -176,3 +176,21 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config"):
         assert k in line
+
+
+def test_chan_combination_of_shard_statistics(built):
+    """The cross-GPU step of the device StandardScaler, on the host: shard statistics combine exactly."""
+    from hybrid_language_music_clustering_vae_b200.scaler import combine_stats, make_sklearn_scaler
+    from sklearn.preprocessing import StandardScaler
+
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((101, 33)) * 5 + 2
+    shards = [X[:10], X[10:64], X[64:64], X[64:]]
+    cnt = [len(s) for s in shards]
+    means = [s.mean(0) if len(s) else np.zeros(33) for s in shards]
+    m2s = [((s - s.mean(0)) ** 2).sum(0) if len(s) else np.zeros(33) for s in shards]
+    n, mean, m2 = combine_stats(cnt, means, m2s)
+    ref = StandardScaler().fit(X)
+    assert n == 101 and np.allclose(mean, ref.mean_) and np.allclose(m2 / n, ref.var_)
+    sc = make_sklearn_scaler(n, mean, m2 / n)
+    assert np.allclose(sc.transform(X), ref.transform(X))

@@ -424,3 +424,35 @@ def test_empty_and_degenerate_batches(built):
     y = hl.synth.synth_batch(1, 5000, seed=2)[0]
     a = ex.extract_host(y)
     assert a["logmel"].shape == (1, 128, 10)
+
+
+def test_device_standard_scaler_matches_sklearn(built, tmp_path):
+    """StandardScaler over the (N, 131072) flattened mel images, statistics and transform on device."""
+    import pickle
+    import torch
+    from sklearn.preprocessing import StandardScaler
+
+    hl = built
+    rng = np.random.default_rng(3)
+    X = (rng.standard_normal((57, 4096)) * rng.uniform(0.1, 30, 4096) - 40.0).astype(np.float32)
+    X[:, 7] = -80.0                      # a constant column (all frames on the top_db floor)
+    ref = StandardScaler()
+    Yr = ref.fit_transform(X)
+    Yd, sc = hl.scaler.fit_transform_device(torch.from_numpy(X).cuda())
+    assert np.allclose(sc.mean_, ref.mean_, rtol=1e-12, atol=1e-12) and np.allclose(sc.var_, ref.var_, rtol=1e-10, atol=1e-12)
+    assert np.array_equal(sc.scale_ == 1.0, ref.scale_ == 1.0) and sc.n_samples_seen_ == 57
+    assert np.abs(Yd.cpu().numpy() - Yr).max() <= 2e-6 * max(1.0, np.abs(Yr).max())
+    assert np.abs(sc.transform(X) - Yr).max() <= 2e-6 * max(1.0, np.abs(Yr).max())     # a genuine sklearn object
+    pickle.loads(pickle.dumps(sc))
+    # shard combination (what the all-reduce computes) == global statistics
+    parts = [X[:20], X[20:41], X[41:]]
+    st = [hl.scaler.column_stats_device(torch.from_numpy(p).cuda()) for p in parts]
+    n, mean, m2 = hl.scaler.combine_stats([len(p) for p in parts], [s[0].cpu().numpy() for s in st],
+                                          [s[1].cpu().numpy() for s in st])
+    assert n == 57 and np.allclose(mean, ref.mean_, rtol=1e-12, atol=1e-12) and np.allclose(m2 / n, ref.var_, rtol=1e-10, atol=1e-12)
+    # through the processed_data2 writer
+    mel = rng.uniform(-80, 0, size=(6, 128, 1024)).astype(np.float32)
+    flat = rng.standard_normal((6, 290))
+    a, _ = hl.preprocessing.save_processed_data2(str(tmp_path / "dev"), mel, flat, np.arange(6), device_scaler=0)
+    b, _ = hl.preprocessing.save_processed_data2(str(tmp_path / "cpu"), mel, flat, np.arange(6))
+    assert a.shape == (6, 128, 1024) and a.dtype == np.float32 and np.abs(a - b).max() <= 5e-6
