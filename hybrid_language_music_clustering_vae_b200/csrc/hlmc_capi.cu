@@ -439,6 +439,112 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         UP(d_fast, blob)
         pl->fast_ok = fast_smem_bytes(ft, 8, N, p.hop_length, nm) <= 227 * 1024;
     }
+    // register-FFT tables for n_fft = 1024 / 512: L = n_fft / 64 lanes per frame (frames_sub kernel)
+    if (N == 1024 || N == 512) {
+        const int Lg = N / 64, Mh = N / 2, PEND = 34 * Lg + 17;
+        FastTables ft{};
+        const int R = (nm + Lg - 1) / Lg;                 // mel rounds: one filter per lane of a group
+        ft.n_groups = R;
+        std::vector<int> meta(2 * R + R * Lg, 0);
+        std::vector<float> melw;
+        auto qof = [](int k) { return k + (k >> 4); };
+        for (int r = 0; r < R; ++r) {
+            std::vector<int> ql(Lg, 0), qlen(Lg, 0), shiftv(Lg, 0);
+            int gmax = 0;
+            for (int l = 0; l < Lg; ++l) {
+                const int m = Lg * r + l;
+                if (m < nm && len[m] > 0) {
+                    ql[l] = qof(lo[m]);
+                    qlen[l] = qof(lo[m] + len[m] - 1) - ql[l] + 1;
+                }
+                gmax = std::max(gmax, qlen[l]);
+            }
+            // as in the 2048 path: shift every lane's first tap down so that the Lg lanes of a group
+            // start on Lg different banks modulo Lg (the groups of a warp are offset by 32 / (32/Lg))
+            int G = (gmax + 3) & ~3;
+            bool ok = (G == 0);
+            for (int tries = 0; !ok && tries < 12; ++tries, G += 4) {
+                std::vector<std::vector<int>> opt(Lg);
+                bool feasible = true;
+                for (int l = 0; l < Lg; ++l) {
+                    if (qlen[l] == 0) { for (int s2 = 0; s2 < Lg; ++s2) opt[l].push_back(-s2); continue; }
+                    const int smin = std::max(0, ql[l] + G - PEND);
+                    const int smax = std::min(G - qlen[l], ql[l]);
+                    if (smin > smax) { feasible = false; break; }
+                    for (int s2 = smin; s2 <= smax && s2 < smin + Lg; ++s2) opt[l].push_back(s2);
+                }
+                if (!feasible) continue;
+                std::vector<int> owner(Lg, -1);
+                auto bank_of = [&](int l, int s2) { return ((qlen[l] == 0 ? -s2 : ql[l] - s2) % Lg + Lg) % Lg; };
+                std::vector<char> seen(Lg);
+                std::function<bool(int)> aug = [&](int l) -> bool {
+                    for (int s2 : opt[l]) {
+                        const int bk = bank_of(l, s2);
+                        if (seen[bk]) continue;
+                        seen[bk] = 1;
+                        if (owner[bk] < 0 || aug(owner[bk])) { owner[bk] = l; return true; }
+                    }
+                    return false;
+                };
+                int matched = 0;
+                for (int l = 0; l < Lg; ++l) { std::fill(seen.begin(), seen.end(), 0); if (aug(l)) ++matched; }
+                if (matched == Lg) {
+                    for (int bk = 0; bk < Lg; ++bk) {
+                        const int l = owner[bk];
+                        for (int s2 : opt[l]) if (bank_of(l, s2) == bk) { shiftv[l] = s2; break; }
+                    }
+                    ok = true;
+                    break;
+                }
+            }
+            if (!ok) {
+                G = (gmax + 3) & ~3;
+                for (int l = 0; l < Lg; ++l) shiftv[l] = std::max(0, ql[l] + G - PEND);
+            }
+            meta[r] = G / 4;
+            meta[R + r] = (int)melw.size();
+            const size_t base = melw.size();
+            melw.resize(base + (size_t)Lg * G, 0.0f);
+            for (int l = 0; l < Lg; ++l) {
+                const int m = Lg * r + l;
+                const int start = (qlen[l] == 0) ? -shiftv[l] : ql[l] - shiftv[l];
+                meta[2 * R + r * Lg + l] = start;
+                if (qlen[l] == 0) continue;
+                for (int q = ql[l]; q < ql[l] + qlen[l]; ++q) {
+                    if (q % 17 == 16) continue;
+                    const int k = q - q / 17, i = q - start;
+                    melw[base + ((size_t)(i / 4) * Lg + l) * 4 + (i % 4)] = pl->mel_dense[(size_t)m * F + k];
+                }
+            }
+        }
+        auto r4 = [](int x) { return (x + 3) & ~3; };
+        ft.win = 0;
+        ft.tw1 = ft.win + N;
+        ft.tw2 = ft.tw1 + 31 * Lg * 2;
+        ft.mel_meta = r4(ft.tw2 + 16 * Lg * 2);
+        ft.mel_w = r4(ft.mel_meta + (int)meta.size());
+        ft.total = r4(ft.mel_w + (int)melw.size());
+        ft.scr = 0;
+        std::vector<float> blob(ft.total, 0.0f);
+        memcpy(&blob[ft.win], win.data(), N * 4);
+        for (int k1 = 1; k1 < 32; ++k1)
+            for (int l = 0; l < Lg; ++l) {
+                const double th = 2.0 * M_PI * double((l * k1) % Mh) / double(Mh);
+                blob[ft.tw1 + ((k1 - 1) * Lg + l) * 2 + 0] = float(cos(th));
+                blob[ft.tw1 + ((k1 - 1) * Lg + l) * 2 + 1] = float(-sin(th));
+            }
+        for (int i = 0; i < 16; ++i)
+            for (int l = 0; l < Lg; ++l) {
+                const double th = 2.0 * M_PI * double(16 * l + i) / double(N);
+                blob[ft.tw2 + (i * Lg + l) * 2 + 0] = float(-sin(th));
+                blob[ft.tw2 + (i * Lg + l) * 2 + 1] = float(-cos(th));
+            }
+        memcpy(&blob[ft.mel_meta], meta.data(), meta.size() * 4);
+        if (!melw.empty()) memcpy(&blob[ft.mel_w], melw.data(), melw.size() * 4);
+        pl->ft = ft;
+        UP(d_fast, blob)
+        pl->fast_ok = sub_smem_bytes(ft, 16, Lg) <= 227 * 1024;
+    }
 #undef UP
     *out = pl;
     return HLMC_OK;
@@ -486,7 +592,8 @@ static int run_frames(hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, 
     if (d_clipmax) CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));
     if (d_status) CK(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
     if (pl->fast_ok && !pl->force_generic && d_spec == nullptr) {
-        CK(launch_frames_fast(a, pl->d_fast, pl->ft, pl->num_sms, st));
+        if (pl->p.n_fft == kFastNfft) CK(launch_frames_fast(a, pl->d_fast, pl->ft, pl->num_sms, st));
+        else CK(launch_frames_sub(a, pl->d_fast, pl->ft, pl->num_sms, st));
     } else {
         if (cand) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs the register-FFT kernel");
         GenericTables gt{pl->d_win, pl->d_twm, pl->d_tws, pl->d_mel_lo, pl->d_mel_len, pl->d_mel_off, pl->d_mel_w};

@@ -79,6 +79,9 @@ struct DbArgs {
 // launchers (all asynchronous on `stream`; return cudaError_t)
 cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                int num_sms, cudaStream_t stream);
+cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
+                              cudaStream_t stream);
+int sub_smem_bytes(const FastTables& ft, int nwarps, int L);
 cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,
                                const FastTables& ft, int num_sms, cudaStream_t stream);
 cudaError_t launch_tuning(const float2* cand, const int* cand_count, int T, int cand_per_frame, long long B,

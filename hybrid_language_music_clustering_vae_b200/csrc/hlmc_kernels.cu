@@ -583,6 +583,385 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
 }
 
 // ---------------------------------------------------------------------------
+// Register-FFT path for n_fft = 1024 and 512.  L = n_fft / 64 lanes (16 or 8) carry one frame,
+// so a warp works on FW = 32 / L consecutive frames of one clip at a time, one per lane group.
+// Same data flow as frames_fast_2048: TMA-staged samples -> 32-point FFT in registers ->
+// transpose -> L-point FFTs -> regroup -> real split -> statistics -> banded mel gather.
+// Every cross-lane step is confined to the group (width-L shuffles, group bits of ballots).
+// ---------------------------------------------------------------------------
+template <int L> struct SubGeom {
+    static constexpr int M = 32 * L;                 // complex FFT length
+    static constexpr int NFFT = 64 * L;
+    static constexpr int FW = 32 / L;                // frames per warp
+    static constexpr int C = 32 / L;                 // pass-2 columns per lane
+    static constexpr int ROWS = 2 * L;               // 16-bin rows of the spectrum
+    static constexpr int GB = (L == 16) ? 1104 : 560;   // floats per group region, == 16 (mod 32)
+    static constexpr int WB = FW * GB;               // floats per warp buffer
+    static constexpr int PEND = 34 * L + 17;         // the kernel keeps group scratch [0, PEND) finite
+};
+
+template <int L> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int d = L / 2; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+template <int L> __device__ __forceinline__ int group_sum_i(int v) {
+#pragma unroll
+    for (int d = L / 2; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+int sub_smem_bytes(const FastTables& ft, int nwarps, int L) {
+    const int wb = (L == 16) ? SubGeom<16>::WB : SubGeom<8>::WB;
+    return (((2 * nwarps + 3) & ~3) + ft.total + nwarps * wb) * 4;
+}
+
+template <int L, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
+    using G = SubGeom<L>;
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NT = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lg = lane & (L - 1), grp = lane / L, gbase = grp * L;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
+    float* tab = smem + ((2 * NW + 3) & ~3);
+    const float2* s_win = reinterpret_cast<const float2*>(tab + ft.win);
+    const float2* s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
+    const float2* s_tw2 = reinterpret_cast<const float2*>(tab + ft.tw2);
+    const int* s_meta = reinterpret_cast<const int*>(tab + ft.mel_meta);
+    const float* s_melw = tab + ft.mel_w;
+    float* wbuf = tab + ft.total + warp * G::WB;
+    float* sc = wbuf + grp * G::GB;                   // this group's region
+    float2* sc2 = reinterpret_cast<float2*>(sc);
+    float* scp = sc + ((L == 8) ? 8 * (grp >> 1) : 0);   // power-spectrum scratch, skewed so groups hit different banks
+
+    for (int i = tid; i < ft.total / 4; i += NT)
+        reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
+    for (int i = tid; i < NW * G::WB; i += NT) (tab + ft.total)[i] = 0.0f;
+    if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncthreads();
+
+    // units of FW consecutive frames; a CTA owns a contiguous run of units, warps take them round-robin
+    const int units_per_clip = (a.T + G::FW - 1) / G::FW;
+    const long long total = (long long)a.B * units_per_clip;
+    const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
+    const long long c0 = (long long)blockIdx.x * per_cta;
+    const long long u1 = (c0 + per_cta < total) ? c0 + per_cta : total;
+    uint32_t parity = 0;
+    float clip_max = 0.0f;
+    const float zthr = a.zcr_thr;
+    const int R = ft.n_groups;                        // mel rounds: ceil(n_mels / L)
+
+    const int zw_base = lg;                           // regroup write: k = lg + L*c + 32*k2
+    const int zlo_base = 17 * lg;
+    const int zhi_base = 17 * (G::ROWS - 1 - lg) + 16;
+    const int zhi0 = (lg == 0) ? 0 : 17 * (G::ROWS - lg);
+
+    for (long long u = c0 + warp; u < u1; u += NW) {
+        const int b = (int)(u / units_per_clip);
+        const int t0 = (int)(u - (long long)b * units_per_clip) * G::FW;
+        const int t = min(t0 + grp, a.T - 1);         // groups past the last frame redo it and are masked
+        const bool live = (t0 + grp) < a.T;
+        const float* clip = a.wave + (long long)b * a.pitch;
+        const int fs = t * a.hop - a.pad;
+        const bool interior = (fs >= 0) && (fs + G::NFFT <= a.n);
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
+        const int shift = (int)((addr & 15) >> 2);
+        const bool fast = __all_sync(FULL, interior && !(shift & 1));
+        int zc_edge = -1;
+        int off;
+        if (fast) {
+            // one bulk copy per group, all completing on the warp's mbarrier
+            const int tot = shift + G::NFFT;
+            const int bulk = tot & ~3;
+            const float* src0 = reinterpret_cast<const float*>(addr & ~uintptr_t(15));
+            if (lg == 0)
+                for (int i = bulk; i < tot; ++i) sc[i] = __ldg(src0 + i);
+            unsigned bytes = (lg == 0) ? (unsigned)bulk * 4u : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(FULL, bytes, d);
+            __syncwarp();
+            if (lg == 0) fence_proxy_async_smem();    // every issuing lane orders its earlier generic accesses
+            if (lane == 0) mbar_arrive_expect_tx(mbar, bytes);
+            __syncwarp();
+            if (lg == 0) tma_bulk_g2s(sc, src0, (unsigned)bulk * 4u, mbar);
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            off = shift;
+        } else {
+            // an edge frame somewhere in the warp: every group builds its padded frame by hand
+            constexpr int CH = G::NFFT / L;           // contiguous samples per lane
+            int zc = 0;
+            float prev = sample_edge(clip, a.n, fs + lg * CH - 1);
+            for (int i = 0; i < CH; ++i) {
+                const int sidx = fs + lg * CH + i;
+                sc[lg * CH + i] = sample_padded(clip, a.n, sidx, a.pad_mode);
+                const float e = sample_edge(clip, a.n, sidx);
+                if ((lg * CH + i) > 0) zc += ((e < -zthr) != (prev < -zthr)) ? 1 : 0;
+                prev = e;
+            }
+            zc_edge = group_sum_i<L>(zc);
+            off = 0;
+            __syncwarp();
+        }
+
+        float vr[64], vi[64];
+        float ss = 0.0f;
+        unsigned za = 0u, zb = 0u;
+        {
+            const float2* xp = reinterpret_cast<const float2*>(sc + off);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float2 x = xp[lg + L * j];
+                const float2 w = s_win[lg + L * j];
+                ss = fmaf(x.x, x.x, ss);
+                ss = fmaf(x.y, x.y, ss);
+                za = __funnelshift_l(__float_as_uint(x.x + zthr), za, 1);
+                zb = __funnelshift_l(__float_as_uint(x.y + zthr), zb, 1);
+                vr[j] = x.x * w.x;
+                vi[j] = x.y * w.y;
+            }
+        }
+        int zc;
+        {
+            unsigned zn = __shfl_sync(FULL, za, gbase + ((lg + 1) & (L - 1)));
+            unsigned msk = FULL;
+            if (lg == L - 1) { zn <<= 1; msk = 0xfffffffeu; }
+            zc = __popc(za ^ zb) + __popc((zb ^ zn) & msk);
+            zc = group_sum_i<L>(zc);
+            if (zc_edge >= 0) zc = zc_edge;
+        }
+        ss = group_sum<L>(ss);
+        __syncwarp();
+
+        // pass 1: 32-point FFT over n1 (z[lg + L*n1]); twiddle W_M^(lg*k1)
+        fftreg::fft_dif<32>(vr, vi);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+            const float2 w = s_tw1[(k1 - 1) * L + lg];
+            const int p = pos32(k1);
+            const float xr = vr[p], xi = vi[p];
+            vr[p] = fmaf(xr, w.x, -(xi * w.y));
+            vi[p] = fmaf(xr, w.y, xi * w.x);
+        }
+        // transpose inside the group: lane lg then owns columns k1 = lg + L*c
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) sc2[lg * 33 + k1] = make_float2(vr[pos32(k1)], vi[pos32(k1)]);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < G::C; ++c)
+#pragma unroll
+            for (int n2 = 0; n2 < L; ++n2) {
+                const float2 v = sc2[n2 * 33 + lg + L * c];
+                vr[c * L + n2] = v.x; vi[c * L + n2] = v.y;
+            }
+        __syncwarp();
+        // pass 2: an L-point FFT per column; bin k = (lg + L*c) + 32*k2 sits at c*L + fft_pos<L>(k2)
+        if constexpr (L == 16) {
+            fftreg::fft_dif<16, 0>(vr, vi);
+            fftreg::fft_dif<16, 16>(vr, vi);
+        } else {
+            fftreg::fft_dif<8, 0>(vr, vi);
+            fftreg::fft_dif<8, 8>(vr, vi);
+            fftreg::fft_dif<8, 16>(vr, vi);
+            fftreg::fft_dif<8, 24>(vr, vi);
+        }
+        // regroup (layout p(k) = k + k/16): lane lg owns bins [16*lg, 16*lg+16) and mirrors M-k
+#pragma unroll
+        for (int c = 0; c < G::C; ++c)
+#pragma unroll
+            for (int k2 = 0; k2 < L; ++k2) {
+                constexpr int dummy = 0; (void)dummy;
+                const int src = c * L + fftreg::fft_pos<L>(k2);
+                sc2[zw_base + (L * c + ((L * c) >> 4)) + 34 * k2] = make_float2(vr[src], vi[src]);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float2 v = sc2[zlo_base + i]; vr[i] = v.x; vi[i] = v.y; }
+        { const float2 v = sc2[zhi0]; vr[16] = v.x; vi[16] = v.y; }
+#pragma unroll
+        for (int i = 1; i < 16; ++i) { const float2 v = sc2[zhi_base - i]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
+        const float2 emid = sc2[17 * L];
+        __syncwarp();
+
+        // real-FFT split, |X|^2, |X|, moments
+        float m0l = 0.f, m1l = 0.f, m0h = 0.f, m1h = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float2 w = s_tw2[i * L + lg];
+            const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
+            const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
+            const float tx = fmaf(w.x, dx, -(w.y * dy));
+            const float ty = fmaf(w.x, dy, w.y * dx);
+            const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
+            const float pk = fmaf(ar, ar, ai * ai);
+            const float pm = fmaf(br, br, bi * bi);
+            const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
+            vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
+            const float d = float(i) - 7.5f;
+            m0l += sk; m1l = fmaf(d, sk, m1l);
+            m0h += sm; m1h = fmaf(-d, sm, m1h);
+        }
+        const float pmid = 4.0f * fmaf(emid.x, emid.x, emid.y * emid.y);
+        const float smid = fast_sqrt(pmid);
+
+        // centroid / bandwidth
+        const float fM = float(G::M);
+        const float kcl = 16.0f * lg + 7.5f;
+        const float kch = fM - 16.0f * lg - 7.5f;
+        float s0 = m0l + m0h;
+        float s1 = fmaf(kcl, m0l, m1l) + fmaf(kch, m0h, m1h);
+        if (lg == L - 1) { s0 += smid; s1 = fmaf(0.5f * fM, smid, s1); }
+        s0 = group_sum<L>(s0);
+        s1 = group_sum<L>(s1);
+        const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;
+        const float cen = s1 / denom;
+        float q = 0.0f;
+        {
+            const float cl = cen - 16.0f * lg;
+            const float ch = (fM - 16.0f * lg) - cen;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float dl = float(i) - cl, dh = ch - float(i);
+                q = fmaf(dl * vi[i], dl, q);
+                q = fmaf(dh * vi[16 + i], dh, q);
+            }
+            if (lg == L - 1) { const float dm = 0.5f * fM - cen; q = fmaf(dm * dm, smid, q); }
+            q = group_sum<L>(q);
+        }
+        const float bw = sqrtf(fmaxf(q, 0.0f) / denom);
+
+        // rolloff
+        int rbin;
+        {
+            constexpr unsigned GM = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+            float pl = m0l;
+#pragma unroll
+            for (int d = 1; d < L; d <<= 1) {
+                const float tv = __shfl_up_sync(FULL, pl, d);
+                if (lg >= d) pl += tv;
+            }
+            float ph = m0h;
+#pragma unroll
+            for (int d = 1; d < L; d <<= 1) {
+                const float tv = __shfl_down_sync(FULL, ph, d);
+                if (lg + d < L) ph += tv;
+            }
+            const float tot_lo = __shfl_sync(FULL, pl, gbase + L - 1);
+            const float tot_hi = __shfl_sync(FULL, ph, gbase);
+            const float mid = tot_lo + smid;
+            const float thr = a.roll_percent * (mid + tot_hi);
+            const unsigned lo_mask = (__ballot_sync(FULL, pl >= thr) >> gbase) & GM;
+            const unsigned hi_mask = (__ballot_sync(FULL, mid + ph >= thr) >> gbase) & GM;
+            // both searches run in every lane (groups may take different branches; keep shuffles converged)
+            float cum = pl - m0l;
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { cum += vi[i]; cnt += (cum < thr) ? 1 : 0; }
+            const int cand_lo = 16 * lg + min(cnt, 15);
+            cum = mid + (ph - m0h);
+            cnt = 0;
+#pragma unroll
+            for (int i = 15; i >= 0; --i) { cum += vi[16 + i]; cnt += (cum < thr) ? 1 : 0; }
+            const int cand_hi = G::M - 16 * lg - (15 - min(cnt, 15));
+            const int tl_lo = lo_mask ? (__ffs(lo_mask) - 1) : 0;
+            const int tl_hi = hi_mask ? (31 - __clz(hi_mask)) : 0;
+            const int r_lo = __shfl_sync(FULL, cand_lo, gbase + tl_lo);
+            const int r_hi = __shfl_sync(FULL, cand_hi, gbase + tl_hi);
+            if (lo_mask) rbin = r_lo;
+            else if (mid >= thr) rbin = G::M / 2;
+            else if (hi_mask) rbin = r_hi;
+            else rbin = G::M;
+        }
+
+        // power (or magnitude) spectrum -> padded scratch of the group
+        {
+            const float* val = a.use_mag ? vi : vr;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) scp[17 * lg + i] = val[i];
+            scp[17 * (G::ROWS - lg)] = val[16];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) scp[17 * (G::ROWS - 1 - lg) + 16 - i] = val[16 + i];
+            if (lg == L - 1) scp[17 * L] = a.use_mag ? smid : pmid;
+            scp[17 * lg + 16] = 0.0f;
+            scp[17 * (G::ROWS - 1 - lg) + 16] = 0.0f;
+            scp[34 * L + 1 + lg] = 0.0f;              // taps past the last bin read zeros
+            if (L == 8) scp[34 * L + 9 + lg] = 0.0f;
+        }
+        __syncwarp();
+
+        // banded mel gather: L filters per round, one per lane of the group
+        if (a.mel_out != nullptr) {
+            float wmax = 0.0f;
+            const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
+            float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
+                                            : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+            for (int r = 0; r < R; ++r) {
+                const int n4 = s_meta[r];
+                const float4* wq = reinterpret_cast<const float4*>(s_melw + s_meta[R + r]) + lg;
+                const float* pq = scp + s_meta[2 * R + r * L + lg];
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                for (int it = 0; it < n4; ++it, wq += L, pq += 4) {
+                    const float4 w = wq[0];
+                    a0 = fmaf(w.x, pq[0], a0);
+                    a1 = fmaf(w.y, pq[1], a1);
+                    a2 = fmaf(w.z, pq[2], a2);
+                    a3 = fmaf(w.w, pq[3], a3);
+                }
+                const float acc = (a0 + a2) + (a1 + a3);
+                const int m = L * r + lg;
+                if (live && m < a.n_mels) outb[(size_t)m * mstride] = acc;
+                if (live) wmax = fmaxf(wmax, acc);
+            }
+            clip_max = fmaxf(clip_max, wmax);
+        }
+        if (lg == 0 && live) {
+            if (a.stats != nullptr) {
+                float* st = a.stats + (size_t)b * 5 * a.T + t;
+                st[0] = cen * a.binhz;
+                st[(size_t)a.T] = bw * a.binhz;
+                st[(size_t)2 * a.T] = float(rbin) * a.binhz;
+                st[(size_t)3 * a.T] = float(zc) * (1.0f / float(G::NFFT));
+                st[(size_t)4 * a.T] = sqrtf(ss * (1.0f / float(G::NFFT)));
+            }
+            if (a.status != nullptr && !(fabsf(ss) <= 3.0e38f)) atomicOr(a.status + b, 1);
+        }
+        // flush the running mel maximum when this warp's next unit belongs to another clip
+        const long long un = u + NW;
+        const bool last = (un >= u1) || ((int)(un / units_per_clip) != b);
+        if (last && a.clipmax != nullptr && a.mel_out != nullptr) {
+            const float m = warp_max(clip_max);
+            if (lane == 0) atomicMax(reinterpret_cast<int*>(a.clipmax) + b, __float_as_int(m));
+            clip_max = 0.0f;
+        }
+        __syncwarp();
+    }
+}
+
+template <int L>
+static cudaError_t launch_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
+                              cudaStream_t stream) {
+    constexpr int NW = 16;
+    const int smem = sub_smem_bytes(ft, NW, L);
+    cudaError_t e = cudaFuncSetAttribute(frames_sub<L, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const long long units = (long long)a.B * ((a.T + SubGeom<L>::FW - 1) / SubGeom<L>::FW);
+    if (units <= 0) return cudaSuccess;
+    long long grid = (units + NW - 1) / NW;
+    if (grid > num_sms) grid = num_sms;
+    frames_sub<L, NW><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    g_launches++;
+    return cudaGetLastError();
+}
+cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
+                              cudaStream_t stream) {
+    if (a.n_fft == 1024) return launch_sub<16>(a, d_tables, ft, num_sms, stream);
+    if (a.n_fft == 512) return launch_sub<8>(a, d_tables, ft, num_sms, stream);
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------
 // librosa.estimate_tuning on the piptrack candidates: median of the magnitudes (exact, by a
 // three-level radix select on the float bits), then the 100-bin histogram of the pitch
 // residuals of the candidates at or above the median; the tuning is the left edge of the

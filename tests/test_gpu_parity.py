@@ -456,3 +456,41 @@ def test_device_standard_scaler_matches_sklearn(built, tmp_path):
     a, _ = hl.preprocessing.save_processed_data2(str(tmp_path / "dev"), mel, flat, np.arange(6), device_scaler=0)
     b, _ = hl.preprocessing.save_processed_data2(str(tmp_path / "cpu"), mel, flat, np.arange(6))
     assert a.shape == (6, 128, 1024) and a.dtype == np.float32 and np.abs(a - b).max() <= 5e-6
+
+
+@pytest.mark.parametrize("n_fft", [1024, 512])
+def test_subwarp_register_fft_kernel(built, n_fft):
+    """n_fft = 1024 / 512 run the frames_sub kernel (16 / 8 lanes per frame, 2 / 4 frames per warp):
+    the same cases the 2048 kernel is put through, plus agreement with the generic kernel."""
+    import torch
+
+    hl = built
+    hop = n_fft // 4
+    assert hl.FeatureExtractor(n_fft=n_fft, hop_length=hop).uses_fast_path()
+    y = hl.synth.synth_batch(12, 20000, seed=n_fft + 1)
+    for kw in (dict(), dict(pad_mode="reflect"), dict(pad_mode="edge"), dict(center=False), dict(hop_length=hop + 37),
+               dict(n_mels=40, n_mfcc=13), dict(n_mels=64, htk=True), dict(win_length=n_fft // 2), dict(window="hamming")):
+        kw = dict(dict(n_fft=n_fft, hop_length=hop, n_mfcc=20), **kw)
+        _check_batch(hl, y, **kw)
+    for n in (1, 2, n_fft // 2 - 1, n_fft - 1, n_fft, n_fft + 1, 3 * n_fft + 5):
+        yy = (0.1 * np.random.default_rng(n).standard_normal((5, n))).astype(np.float32)
+        res = _check_batch(hl, yy, n_fft=n_fft, hop_length=hop, n_mfcc=13, pad_mode="reflect")
+        assert res["logmel"].shape[-1] == 1 + n // hop
+    for extra in (1, 2, 3):
+        _check_batch(hl, hl.synth.synth_batch(5, 6001, seed=4), pitch=6001 + extra, n_fft=n_fft, hop_length=hop, n_mfcc=13)
+    # bitwise independence of batch composition, and agreement with the shared-memory FFT kernel
+    ex = hl.FeatureExtractor(n_fft=n_fft, hop_length=hop, n_mfcc=20, ref=np.max)
+    yd = torch.from_numpy(hl.synth.synth_batch(64, 30000, seed=9)).cuda()
+    a = {k: v.clone() for k, v in ex.extract_device(yd).items()}
+    idx = torch.tensor([63, 5, 17], device="cuda")
+    c = ex.extract_device(yd[idx].contiguous())
+    for k in ("logmel", "mfcc", "stats"):
+        assert torch.equal(c[k], a[k][idx]), k
+    ex.force_generic(True)
+    gk = ex.extract_device(yd)
+    assert (gk["logmel"] - a["logmel"]).abs().max() <= LOGMEL_TOL_DB     # two float32 FFTs, each within tolerance
+    assert (gk["mfcc"] - a["mfcc"]).abs().max() <= 1e-4 * float(a["mfcc"].abs().max())
+    bad = yd.clone()
+    bad[3, 100] = float("nan")
+    ex.force_generic(False)
+    assert ex.extract_device(bad)["status"].cpu().tolist() == [0, 0, 0, 1] + [0] * 60
