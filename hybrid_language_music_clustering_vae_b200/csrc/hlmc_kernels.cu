@@ -146,6 +146,42 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Banded mel gather of one (group, lane): n4 float4 steps of 4 taps each.  The step count is
+// warp-uniform but only known at run time, so the steps are fully unrolled behind a switch with
+// fall-through (one indirect branch per group instead of a counted loop: the loop control used to
+// cost as many issue slots as the multiply-adds).
+#define HLMC_MEL_STEP(S)                                        \
+    {                                                           \
+        const float4 w = wp[32 * (S)];                          \
+        a0 = fmaf(w.x, pp[4 * (S) + 0], a0);                    \
+        a1 = fmaf(w.y, pp[4 * (S) + 1], a1);                    \
+        a2 = fmaf(w.z, pp[4 * (S) + 2], a2);                    \
+        a3 = fmaf(w.w, pp[4 * (S) + 3], a3);                    \
+    }
+__device__ __forceinline__ void mel_steps(int n4, const float4* __restrict__ wp, const float* __restrict__ pp,
+                                          float& a0, float& a1, float& a2, float& a3) {
+    for (; n4 > 16; --n4) HLMC_MEL_STEP(n4 - 1)
+    switch (n4) {
+        case 16: HLMC_MEL_STEP(15)
+        case 15: HLMC_MEL_STEP(14)
+        case 14: HLMC_MEL_STEP(13)
+        case 13: HLMC_MEL_STEP(12)
+        case 12: HLMC_MEL_STEP(11)
+        case 11: HLMC_MEL_STEP(10)
+        case 10: HLMC_MEL_STEP(9)
+        case 9: HLMC_MEL_STEP(8)
+        case 8: HLMC_MEL_STEP(7)
+        case 7: HLMC_MEL_STEP(6)
+        case 6: HLMC_MEL_STEP(5)
+        case 5: HLMC_MEL_STEP(4)
+        case 4: HLMC_MEL_STEP(3)
+        case 3: HLMC_MEL_STEP(2)
+        case 2: HLMC_MEL_STEP(1)
+        case 1: HLMC_MEL_STEP(0)
+        default: break;
+    }
+}
+
 struct WarpState {
     float* sc;                 // this warp's shared buffer (TMA landing zone, then scratch)
     float2* sc2;
@@ -158,12 +194,12 @@ struct WarpState {
 // One frame, from samples to spectrum, shared by the feature kernel and the chroma kernel.
 // On return vr[i] / vi[i] hold |X|^2 / |X| of bin 16*lane + i (i < 16) and of bin
 // 1024 - 16*lane - (i - 16) (i >= 16); p512 / s512 are bin 512; ss = sum of squares of the
-// frame's samples, zc = zero crossings; m0*/m1* are the lane's magnitude moments about the
-// centres of its two 16-bin runs.
+// frame's samples, zc = zero crossings; m0*/m1*/m2* are the lane's magnitude moments (orders 0-2)
+// about the centres of its two 16-bin runs.
 __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
                                                float (&vr)[64], float (&vi)[64], float& p512, float& s512,
-                                               float& ss, int& zc, float& m0l, float& m1l, float& m0h,
-                                               float& m1h) {
+                                               float& ss, int& zc, float& m0l, float& m1l, float& m2l,
+                                               float& m0h, float& m1h, float& m2h) {
     float* const sc = w.sc;
     float2* const sc2 = w.sc2;
     uint64_t* const mbar = w.mbar;
@@ -281,7 +317,7 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     __syncwarp();
 
     // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
-    m0l = 0.f; m1l = 0.f; m0h = 0.f; m1h = 0.f;
+    m0l = 0.f; m1l = 0.f; m2l = 0.f; m0h = 0.f; m1h = 0.f; m2h = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const float2 w = s_tw2[i * 32 + lane];
@@ -295,8 +331,8 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
         const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
         vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
         const float d = float(i) - 7.5f;
-        m0l += sk; m1l = fmaf(d, sk, m1l);
-        m0h += sm; m1h = fmaf(-d, sm, m1h);
+        m0l += sk; m1l = fmaf(d, sk, m1l); m2l = fmaf(d * d, sk, m2l);
+        m0h += sm; m1h = fmaf(-d, sm, m1h); m2h = fmaf(d * d, sm, m2h);
     }
     // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
     p512 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
@@ -356,9 +392,9 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     for (long long g = g0; g < g1; g += NW) {
         const float* clip = a.wave + (long long)b * a.pitch;
         float vr[64], vi[64];
-        float p512, s512, ss, m0l, m1l, m0h, m1h;
+        float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
         int zc;
-        frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m0h, m1h);
+        frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
 
         // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
         const float kcl = 16.0f * lane + 7.5f;
@@ -370,18 +406,14 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         s1 = warp_sum(s1);
         const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;   // util.normalize tiny guard
         const float cen = s1 / denom;                            // in bins
-        // second pass over the magnitudes held in registers: sum |X| (k - centroid)^2, the
-        // two-pass form librosa uses (one-pass moment algebra cancels badly for narrow spectra)
-        float q = 0.0f;
+        // sum |X| (k - centroid)^2 from the moments about the run centres: with d = k - kc,
+        // sum s (d + (kc - c))^2 = m2 + 2 (kc - c) m1 + (kc - c)^2 m0.  |d| <= 7.5, so the cancellation
+        // that rules out one-pass moments about the origin (k up to 1024) is bounded by a few tens of
+        // ulps of the lane's own energy; librosa's two-pass form differs by < 1e-5 bins^2.
+        float q;
         {
-            const float cl = cen - 16.0f * lane;                 // k - c = i - cl        (low run)
-            const float ch = (1024.0f - 16.0f * lane) - cen;     // k - c = ch - i        (high run)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float dl = float(i) - cl, dh = ch - float(i);
-                q = fmaf(dl * vi[i], dl, q);
-                q = fmaf(dh * vi[16 + i], dh, q);
-            }
+            const float dl = kcl - cen, dh = kch - cen;
+            q = fmaf(dl, fmaf(dl, m0l, 2.0f * m1l), m2l) + fmaf(dh, fmaf(dh, m0h, 2.0f * m1h), m2h);
             if (lane == 31) { const float dm = 512.0f - cen; q = fmaf(dm * dm, s512, q); }
             q = warp_sum(q);
         }
@@ -502,25 +534,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 const float4* wp = reinterpret_cast<const float4*>(s_melw + s_meta[kMaxMelGroups + g]) + lane;
                 const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * g + lane];
                 float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                int i4 = 0;
-                for (; i4 + 2 <= n4; i4 += 2) {
-                    const float4 w = wp[32 * i4], v = wp[32 * i4 + 32];
-                    a0 = fmaf(w.x, pp[4 * i4 + 0], a0);
-                    a1 = fmaf(w.y, pp[4 * i4 + 1], a1);
-                    a2 = fmaf(w.z, pp[4 * i4 + 2], a2);
-                    a3 = fmaf(w.w, pp[4 * i4 + 3], a3);
-                    a0 = fmaf(v.x, pp[4 * i4 + 4], a0);
-                    a1 = fmaf(v.y, pp[4 * i4 + 5], a1);
-                    a2 = fmaf(v.z, pp[4 * i4 + 6], a2);
-                    a3 = fmaf(v.w, pp[4 * i4 + 7], a3);
-                }
-                if (i4 < n4) {
-                    const float4 w = wp[32 * i4];
-                    a0 = fmaf(w.x, pp[4 * i4 + 0], a0);
-                    a1 = fmaf(w.y, pp[4 * i4 + 1], a1);
-                    a2 = fmaf(w.z, pp[4 * i4 + 2], a2);
-                    a3 = fmaf(w.w, pp[4 * i4 + 3], a3);
-                }
+                mel_steps(n4, wp, pp, a0, a1, a2, a3);
                 a0 += a2; a1 += a3;
                 const float acc = a0 + a1;
                 const int m = 32 * g + lane;
@@ -1144,9 +1158,9 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
         const float* clip = a.wave + (long long)b * a.pitch;
         for (int t = warp; t < a.T; t += NW) {
             float vr[64], vi[64];
-            float p512, s512, ss, m0l, m1l, m0h, m1h;
+            float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
             int zc;
-            frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m0h, m1h);
+            frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
             float raw[kChroma];
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) {
@@ -1358,68 +1372,140 @@ cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, c
 // subtraction, so db10(max) - db10(max) is exactly 0 (librosa: ref=np.max peaks at 0.0 dB)
 __device__ __forceinline__ float db10(float x) { return __fmul_rn(3.0102999566398120f, __log2f(x)); }
 
+constexpr int kDbThreads = 128;
+// frames per thread: every shared-memory broadcast of a DCT row feeds 2x the FMAs (while the accumulators fit)
+__host__ __device__ constexpr int db_frames(int nc) { return nc <= 40 ? 2 : 1; }
+
 template <int NC>
-__global__ void __launch_bounds__(128) db_dct(const DbArgs a) {
+__global__ void __launch_bounds__(kDbThreads, (NC <= 40) ? 4 : 1) db_dct(const DbArgs a) {
+    // The DCT-II basis is symmetric (even k) / antisymmetric (odd k) about the middle of the mel axis:
+    // cos(pi (2(N-1-n)+1) k / 2N) = (-1)^k cos(pi (2n+1) k / 2N).  Folding the input into
+    // s_n = x_n + x_(N-1-n) and d_n = x_n - x_(N-1-n) halves the multiply-adds: even coefficients
+    // come from s, odd ones from d.  sD[n][j]: j < NC/2 -> coefficient 2j, else coefficient 2(j-NC/2)+1.
+    // The table is read as warp-wide 16-byte broadcasts, which cost 4 shared-memory cycles each; with
+    // one frame per thread that pipe, not the FMA pipe, bounds the kernel - hence kDbFrames frames per thread.
     extern __shared__ __align__(16) float sD[];
-    if (NC > 0) {
-        for (int i = threadIdx.x; i < a.n_mels * NC; i += 128) sD[i] = a.dct_t[i];
+    constexpr int H = NC / 2;
+    constexpr int F = db_frames(NC);
+    const int half = a.n_mels >> 1;                 // mirrored pairs; an odd n_mels has a middle row
+    if constexpr (NC > 0) {
+        const int rows = (a.n_mels + 1) >> 1;
+        for (int i = threadIdx.x; i < rows * NC; i += kDbThreads) {
+            const int n = i / NC, j = i - n * NC;
+            const int c = (j < H) ? 2 * j : 2 * (j - H) + 1;
+            sD[i] = a.dct_t[n * NC + c];
+        }
         __syncthreads();
     }
-    const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (g >= (long long)a.B * a.T) return;
-    const int b = (int)(g / a.T), t = (int)(g - (long long)b * a.T);
-    const float pmax = __uint_as_float(a.clipmax[b]);
-    const float maxa = db10(fmaxf(a.amin, pmax));
-    const float ref_db = (a.ref_mode == 1) ? maxa : db10(fmaxf(a.amin, fabsf(a.ref_value)));
-    const float floor_db = (a.top_db >= 0.0f) ? (maxa - ref_db) - a.top_db : -CUDART_INF_F;
+    const long long total = (long long)a.B * a.T;
     // librosa.feature.mfcc always calls power_to_db(S) with ref=1.0, amin=1e-10, top_db=80
     const bool same_amin = (a.amin == 1e-10f);
-    const float floor_m = db10(fmaxf(1e-10f, pmax)) - 80.0f;
-    float acc[NC > 0 ? NC : 1];
+    bool live[F];
+    float ref_db[F], floor_db[F], floor_m[F];
+    float* col[F];
+    const float* row[F];
+    size_t mfcc_off[F];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] = 0.0f;
-    float* col = a.mel + (size_t)b * a.n_mels * a.T + t;
-    const float* row = a.mel_in ? a.mel_in + ((size_t)b * a.T + t) * a.n_mels : nullptr;
-    const bool vec = (row != nullptr) && ((a.n_mels & 3) == 0);
-    constexpr int MB = 8;                       // mel rows fetched per batch: 8 independent loads in flight
-    for (int m0 = 0; m0 < a.n_mels; m0 += MB) {
-        float pv[MB];
-        if (vec && m0 + MB <= a.n_mels) {       // frame-major scratch: two 16-byte loads
-            const float4 u = __ldg(reinterpret_cast<const float4*>(row + m0));
-            const float4 v = __ldg(reinterpret_cast<const float4*>(row + m0 + 4));
-            pv[0] = u.x; pv[1] = u.y; pv[2] = u.z; pv[3] = u.w; pv[4] = v.x; pv[5] = v.y; pv[6] = v.z; pv[7] = v.w;
-        } else {
+    for (int f = 0; f < F; ++f) {
+        // thread i of the block takes frames i and i + 128 of the block's 256: stores stay coalesced
+        long long g = ((long long)blockIdx.x * F + f) * kDbThreads + threadIdx.x;
+        live[f] = g < total;
+        if (!live[f]) g = total - 1;                // compute on a valid frame, skip the stores
+        const int b = (int)(g / a.T), t = (int)(g - (long long)b * a.T);
+        const float pmax = __uint_as_float(a.clipmax[b]);
+        const float maxa = db10(fmaxf(a.amin, pmax));
+        ref_db[f] = (a.ref_mode == 1) ? maxa : db10(fmaxf(a.amin, fabsf(a.ref_value)));
+        floor_db[f] = (a.top_db >= 0.0f) ? (maxa - ref_db[f]) - a.top_db : -CUDART_INF_F;
+        floor_m[f] = db10(fmaxf(1e-10f, pmax)) - 80.0f;
+        col[f] = a.mel + (size_t)b * a.n_mels * a.T + t;
+        row[f] = a.mel_in ? a.mel_in + ((size_t)b * a.T + t) * a.n_mels : nullptr;
+        mfcc_off[f] = (size_t)b * a.n_mfcc * a.T + t;
+    }
+    if (!live[0]) return;
+    float acc[F][NC > 0 ? NC : 1];
 #pragma unroll
-            for (int j = 0; j < MB; ++j)
-                pv[j] = (m0 + j < a.n_mels) ? (row ? row[m0 + j] : col[(size_t)(m0 + j) * a.T]) : 0.0f;
+    for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[f][c] = 0.0f;
+    const bool vec = (a.mel_in != nullptr) && ((a.n_mels & 7) == 0);
+    // one mel row: dB for the log-mel output, the (ref = 1, top_db = 80) dB value for the DCT
+    auto to_db = [&](int f, float p, int m) -> float {
+        const float adb = db10(fmaxf(a.amin, p));
+        if (live[f]) col[f][(size_t)m * a.T] = fmaxf(adb - ref_db[f], floor_db[f]);
+        const float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
+        return fmaxf(x, floor_m[f]);
+    };
+    auto fetch = [&](int f, int m) -> float { return row[f] ? row[f][m] : col[f][(size_t)m * a.T]; };
+    constexpr int MB = 4;                           // mirrored pairs per batch: 8 values per frame in flight
+    for (int n0 = 0; n0 < half; n0 += MB) {
+        float lo[F][MB], hi[F][MB];                 // lo[j] = row n0 + j, hi[j] = row N-1-(n0+j)
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            if (vec) {                              // frame-major scratch: two 16-byte loads
+                const float4 u = __ldg(reinterpret_cast<const float4*>(row[f] + n0));
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row[f] + a.n_mels - MB - n0));
+                lo[f][0] = u.x; lo[f][1] = u.y; lo[f][2] = u.z; lo[f][3] = u.w;
+                hi[f][0] = v.w; hi[f][1] = v.z; hi[f][2] = v.y; hi[f][3] = v.x;
+            } else {
+#pragma unroll
+                for (int j = 0; j < MB; ++j) {
+                    const bool in = n0 + j < half;
+                    lo[f][j] = in ? fetch(f, n0 + j) : 0.0f;
+                    hi[f][j] = in ? fetch(f, a.n_mels - 1 - n0 - j) : 0.0f;
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < MB; ++j) {
-            const int m = m0 + j;
-            if (m >= a.n_mels) break;
-            const float p = pv[j];
-            const float adb = db10(fmaxf(a.amin, p));
-            col[(size_t)m * a.T] = fmaxf(adb - ref_db, floor_db);
-            if (NC > 0) {
-                float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
-                x = fmaxf(x, floor_m);
-                const float4* d4 = reinterpret_cast<const float4*>(sD + m * NC);
+            const int n = n0 + j;
+            if (n >= half) break;
+            float s[F], d[F];
 #pragma unroll
-                for (int c = 0; c < NC / 4; ++c) {
-                    const float4 d = d4[c];
-                    acc[4 * c + 0] = fmaf(d.x, x, acc[4 * c + 0]);
-                    acc[4 * c + 1] = fmaf(d.y, x, acc[4 * c + 1]);
-                    acc[4 * c + 2] = fmaf(d.z, x, acc[4 * c + 2]);
-                    acc[4 * c + 3] = fmaf(d.w, x, acc[4 * c + 3]);
+            for (int f = 0; f < F; ++f) {
+                const float xl = to_db(f, lo[f][j], n), xh = to_db(f, hi[f][j], a.n_mels - 1 - n);
+                s[f] = xl + xh; d[f] = xl - xh;
+            }
+            if constexpr (NC > 0) {
+                const float4* d4 = reinterpret_cast<const float4*>(sD + n * NC);
+#pragma unroll
+                for (int c = 0; c < H / 4; ++c) {
+                    const float4 e = d4[c], o = d4[H / 4 + c];
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+                        acc[f][4 * c + 0] = fmaf(e.x, s[f], acc[f][4 * c + 0]);
+                        acc[f][4 * c + 1] = fmaf(e.y, s[f], acc[f][4 * c + 1]);
+                        acc[f][4 * c + 2] = fmaf(e.z, s[f], acc[f][4 * c + 2]);
+                        acc[f][4 * c + 3] = fmaf(e.w, s[f], acc[f][4 * c + 3]);
+                        acc[f][H + 4 * c + 0] = fmaf(o.x, d[f], acc[f][H + 4 * c + 0]);
+                        acc[f][H + 4 * c + 1] = fmaf(o.y, d[f], acc[f][H + 4 * c + 1]);
+                        acc[f][H + 4 * c + 2] = fmaf(o.z, d[f], acc[f][H + 4 * c + 2]);
+                        acc[f][H + 4 * c + 3] = fmaf(o.w, d[f], acc[f][H + 4 * c + 3]);
+                    }
                 }
             }
         }
     }
-    if (NC > 0) {
-        float* mo = a.mfcc + (size_t)b * a.n_mfcc * a.T + t;
+    if (a.n_mels & 1) {                             // middle row: odd coefficients vanish there
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-            if (c < a.n_mfcc) mo[(size_t)c * a.T] = acc[c];
+        for (int f = 0; f < F; ++f) {
+            const float x = to_db(f, fetch(f, half), half);
+            if constexpr (NC > 0) {
+#pragma unroll
+                for (int c = 0; c < H; ++c) acc[f][c] = fmaf(sD[half * NC + c], x, acc[f][c]);
+            }
+        }
+    }
+    if constexpr (NC > 0) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            if (!live[f]) continue;
+            float* mo = a.mfcc + mfcc_off[f];
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                if (2 * j < a.n_mfcc) mo[(size_t)(2 * j) * a.T] = acc[f][j];
+                if (2 * j + 1 < a.n_mfcc) mo[(size_t)(2 * j + 1) * a.T] = acc[f][H + j];
+            }
+        }
     }
 }
 
@@ -1427,12 +1513,13 @@ template <int NC>
 static cudaError_t launch_db_nc(const DbArgs& a, cudaStream_t stream) {
     const long long frames = (long long)a.B * a.T;
     if (frames <= 0) return cudaSuccess;
-    const int smem = a.n_mels * NC * 4;
+    const int smem = ((a.n_mels + 1) / 2) * NC * 4;   // folded DCT table
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(db_dct<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    db_dct<NC><<<(unsigned)((frames + 127) / 128), 128, smem, stream>>>(a);
+    const long long per_block = (long long)kDbThreads * db_frames(NC);
+    db_dct<NC><<<(unsigned)((frames + per_block - 1) / per_block), kDbThreads, smem, stream>>>(a);
     g_launches++;
     return cudaGetLastError();
 }
