@@ -21,6 +21,7 @@
 #include <atomic>
 
 #include "fft_inreg.cuh"
+#include "fft_inreg2.cuh"
 #include "hlmc_internal.h"
 
 namespace hlmc {
@@ -192,12 +193,13 @@ struct WarpState {
 };
 
 // One frame, from samples to spectrum, shared by the feature kernel and the chroma kernel.
-// On return vr[i] / vi[i] hold |X|^2 / |X| of bin 16*lane + i (i < 16) and of bin
-// 1024 - 16*lane - (i - 16) (i >= 16); p512 / s512 are bin 512; ss = sum of squares of the
-// frame's samples, zc = zero crossings; m0*/m1*/m2* are the lane's magnitude moments (orders 0-2)
-// about the centres of its two 16-bin runs.
+// On return P[i] / S[i] hold |X|^2 / |X| of bin 16*lane + i (.x, the lane's low run) and of bin
+// 1024 - 16*lane - i (.y, its mirrored high run); p512 / s512 are bin 512; ss = sum of squares of
+// the frame's samples, zc = zero crossings; m0*/m1*/m2* are the lane's magnitude moments (orders
+// 0-2) about the centres of its two 16-bin runs.
+// All complex arithmetic is packed FP32 (FADD2 / FMUL2 / FFMA2): one float2 = (re, im).
 __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
-                                               float (&vr)[64], float (&vi)[64], float& p512, float& s512,
+                                               float2 (&P)[16], float2 (&S)[16], float& p512, float& s512,
                                                float& ss, int& zc, float& m0l, float& m1l, float& m2l,
                                                float& m0h, float& m1h, float& m2h) {
     float* const sc = w.sc;
@@ -247,24 +249,26 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
         __syncwarp();
     }
 
-    ss = 0.0f;
     unsigned za = 0u, zb = 0u;
+    float2 v[32];
 
     // ---- phase 0: frame -> registers; window; RMS and ZCR partials
     {
         const float2* xp = reinterpret_cast<const float2*>(sc + off);
+        const float2 zt = make_float2(zthr, zthr);
+        float2 ss2 = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const float2 x = xp[lane + 32 * j];
-            const float2 w = s_win[lane + 32 * j];
-            ss = fmaf(x.x, x.x, ss);
-            ss = fmaf(x.y, x.y, ss);
+            const float2 wn = s_win[lane + 32 * j];
+            ss2 = __ffma2_rn(x, x, ss2);
             // sign bit of (x + thr) <=> x < -thr; sample j ends up at bit 31 - j
-            za = __funnelshift_l(__float_as_uint(x.x + zthr), za, 1);
-            zb = __funnelshift_l(__float_as_uint(x.y + zthr), zb, 1);
-            vr[j] = x.x * w.x;
-            vi[j] = x.y * w.y;
+            const float2 xt = __fadd2_rn(x, zt);
+            za = __funnelshift_l(__float_as_uint(xt.x), za, 1);
+            zb = __funnelshift_l(__float_as_uint(xt.y), zb, 1);
+            v[j] = __fmul2_rn(x, wn);
         }
+        ss = ss2.x + ss2.y;
     }
     {
         // pairs (2m, 2m+1) sit in one lane; pairs (2m+1, 2m+2) straddle to the next lane
@@ -279,61 +283,62 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     __syncwarp();                       // every lane has its samples: the buffer becomes scratch
 
     // ---- phase 1: 32-point FFT over n1 (this lane holds z[lane + 32*n1])
-    fftreg::fft_dif<32>(vr, vi);
+    fftreg2::fft_dif<32>(v);
 
-    // ---- phase 2: inter-pass twiddle W_1024^(lane*k1)
+    // ---- phase 2: inter-pass twiddle W_1024^(lane*k1); the table holds (cos, -sin)
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 w = s_tw1[(k1 - 1) * 32 + lane];
+        const float2 tw = s_tw1[(k1 - 1) * 32 + lane];
         const int p = pos32(k1);
-        const float xr = vr[p], xi = vi[p];
-        vr[p] = fmaf(xr, w.x, -(xi * w.y));
-        vi[p] = fmaf(xr, w.y, xi * w.x);
+        v[p] = fftreg2::cmul(v[p], tw.x, tw.y);
     }
 
     // ---- phase 3: 32x32 complex transpose through shared memory
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) sc2[lane * 33 + k1] = make_float2(vr[pos32(k1)], vi[pos32(k1)]);
+    for (int k1 = 0; k1 < 32; ++k1) sc2[lane * 33 + k1] = v[pos32(k1)];
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) { const float2 v = sc2[n2 * 33 + lane]; vr[n2] = v.x; vi[n2] = v.y; }
+    for (int n2 = 0; n2 < 32; ++n2) v[n2] = sc2[n2 * 33 + lane];
     __syncwarp();
 
     // ---- phase 4: 32-point FFT over n2; lane = k1, bin k = k1 + 32*k2 at pos32(k2)
-    fftreg::fft_dif<32>(vr, vi);
+    fftreg2::fft_dif<32>(v);
 
-    // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) and their
-    //      mirrors 1024-k
+    // ---- phase 5: regroup so each lane owns bins [16*lane, 16*lane+16) (v[0..15]) and their
+    //      mirrors 1024-k (v[16..31])
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2)
-        sc2[zw_base + 34 * k2] = make_float2(vr[pos32(k2)], vi[pos32(k2)]);
+    for (int k2 = 0; k2 < 32; ++k2) sc2[zw_base + 34 * k2] = v[pos32(k2)];
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const float2 v = sc2[zlo_base + i]; vr[i] = v.x; vi[i] = v.y; }
-    { const float2 v = sc2[zhi0]; vr[16] = v.x; vi[16] = v.y; }
+    for (int i = 0; i < 16; ++i) v[i] = sc2[zlo_base + i];
+    v[16] = sc2[zhi0];
 #pragma unroll
-    for (int i = 1; i < 16; ++i) { const float2 v = sc2[zhi_base - i]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
+    for (int i = 1; i < 16; ++i) v[16 + i] = sc2[zhi_base - i];
     const float2 e512 = sc2[544];
     __syncwarp();
 
     // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
-    m0l = 0.f; m1l = 0.f; m2l = 0.f; m0h = 0.f; m1h = 0.f; m2h = 0.f;
+    float2 M0 = make_float2(0.f, 0.f), M1 = M0, M2 = M0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const float2 w = s_tw2[i * 32 + lane];
-        const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
-        const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
-        const float tx = fmaf(w.x, dx, -(w.y * dy));
-        const float ty = fmaf(w.x, dy, w.y * dx);
-        const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
-        const float pk = fmaf(ar, ar, ai * ai);
-        const float pm = fmaf(br, br, bi * bi);
-        const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
-        vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
-        const float d = float(i) - 7.5f;
-        m0l += sk; m1l = fmaf(d, sk, m1l); m2l = fmaf(d * d, sk, m2l);
-        m0h += sm; m1h = fmaf(-d, sm, m1h); m2h = fmaf(d * d, sm, m2h);
+        const float2 tw = s_tw2[i * 32 + lane];
+        const float2 za_ = v[i], zb_ = v[16 + i];
+        const float2 e = __fadd2_rn(za_, make_float2(zb_.x, -zb_.y));      // Z[k] + conj Z[1024-k]
+        const float2 d = __fadd2_rn(za_, make_float2(-zb_.x, zb_.y));      // Z[k] - conj Z[1024-k]
+        const float2 tt = fftreg2::cmul(d, tw.x, tw.y);
+        // X[k] = e + t, conj X[1024-k] = e - t; pair the real parts and the imaginary parts
+        const float2 R = __fadd2_rn(make_float2(e.x, e.x), make_float2(tt.x, -tt.x));
+        const float2 I = __fadd2_rn(make_float2(e.y, e.y), make_float2(tt.y, -tt.y));
+        const float2 pw = __ffma2_rn(R, R, __fmul2_rn(I, I));              // (|X[k]|^2, |X[1024-k]|^2)
+        const float2 sq = make_float2(fast_sqrt(pw.x), fast_sqrt(pw.y));
+        P[i] = pw;
+        S[i] = sq;
+        const float dd = float(i) - 7.5f;
+        M0 = __fadd2_rn(M0, sq);
+        M1 = __ffma2_rn(make_float2(sq.x, -sq.y), make_float2(dd, dd), M1);
+        M2 = __ffma2_rn(sq, make_float2(dd * dd, dd * dd), M2);
     }
+    m0l = M0.x; m0h = M0.y; m1l = M1.x; m1h = M1.y; m2l = M2.x; m2h = M2.y;
     // bin 512 pairs with itself: X[512] = 2*conj(Zhalf[512])
     p512 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
     s512 = fast_sqrt(p512);
@@ -391,10 +396,10 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
 
     for (long long g = g0; g < g1; g += NW) {
         const float* clip = a.wave + (long long)b * a.pitch;
-        float vr[64], vi[64];
+        float2 P[16], S[16];
         float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
         int zc;
-        frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
+        frame_spectrum(a, w, clip, t, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
 
         // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
         const float kcl = 16.0f * lane + 7.5f;
@@ -445,7 +450,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 float cum = pl - m0l;
                 int cnt = 0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { cum += vi[i]; cnt += (cum < thr) ? 1 : 0; }
+                for (int i = 0; i < 16; ++i) { cum += S[i].x; cnt += (cum < thr) ? 1 : 0; }
                 rbin = __shfl_sync(FULL, 16 * lane + min(cnt, 15), tl);
             } else if (mid >= thr) {
                 rbin = 512;
@@ -456,7 +461,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                     float cum = mid + (ph - m0h);
                     int cnt = 0;
 #pragma unroll
-                    for (int i = 15; i >= 0; --i) { cum += vi[16 + i]; cnt += (cum < thr) ? 1 : 0; }
+                    for (int i = 15; i >= 0; --i) { cum += S[i].y; cnt += (cum < thr) ? 1 : 0; }
                     // ascending bins are i = 15..0: the cnt-th of them is i = 15 - cnt
                     rbin = __shfl_sync(FULL, 1024 - 16 * lane - (15 - min(cnt, 15)), tl);
                 } else {
@@ -468,17 +473,17 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         // ---- phase 7: power (or magnitude) spectrum -> padded scratch, q(k) = k + k/16
         if (a.use_mag) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vi[i];
-            sc[17 * (64 - lane)] = vi[16];
+            for (int i = 0; i < 16; ++i) sc[17 * lane + i] = S[i].x;
+            sc[17 * (64 - lane)] = S[0].y;
 #pragma unroll
-            for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vi[16 + i];
+            for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = S[i].y;
             if (lane == 31) sc[544] = s512;
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sc[17 * lane + i] = vr[i];
-            sc[17 * (64 - lane)] = vr[16];
+            for (int i = 0; i < 16; ++i) sc[17 * lane + i] = P[i].x;
+            sc[17 * (64 - lane)] = P[0].y;
 #pragma unroll
-            for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = vr[16 + i];
+            for (int i = 1; i < 16; ++i) sc[17 * (63 - lane) + 16 - i] = P[i].y;
             if (lane == 31) sc[544] = p512;
         }
         sc[17 * lane + 16] = 0.0f;
@@ -491,7 +496,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         if (PIP) {
             float pmax = p512;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pmax = fmaxf(pmax, vr[i]);
+            for (int i = 0; i < 16; ++i) pmax = fmaxf(pmax, fmaxf(P[i].x, P[i].y));
             pmax = warp_max(pmax);
             const float ref = a.pip_threshold * pmax;
             // every frame owns a fixed block of cand_cap slots (at most every other bin of the band
@@ -1157,10 +1162,12 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
         __syncthreads();
         const float* clip = a.wave + (long long)b * a.pitch;
         for (int t = warp; t < a.T; t += NW) {
-            float vr[64], vi[64];
+            float2 P[16], S[16];
             float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
             int zc;
-            frame_spectrum(a, w, clip, t, vr, vi, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
+            frame_spectrum(a, w, clip, t, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
+            // filterbank column j of this lane: j < 16 -> bin 16*lane + j, else bin 1024 - 16*lane - (j - 16)
+            auto pw = [&](int j) -> float { return j < 16 ? P[j].x : P[j - 16].y; };
             float raw[kChroma];
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) {
@@ -1169,10 +1176,10 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                     const float4 f = fp[j4 * 32];
-                    a0 = fmaf(f.x, vr[4 * j4 + 0], a0);
-                    a1 = fmaf(f.y, vr[4 * j4 + 1], a1);
-                    a0 = fmaf(f.z, vr[4 * j4 + 2], a0);
-                    a1 = fmaf(f.w, vr[4 * j4 + 3], a1);
+                    a0 = fmaf(f.x, pw(4 * j4 + 0), a0);
+                    a1 = fmaf(f.y, pw(4 * j4 + 1), a1);
+                    a0 = fmaf(f.z, pw(4 * j4 + 2), a0);
+                    a1 = fmaf(f.w, pw(4 * j4 + 3), a1);
                 }
                 float r = a0 + a1;
                 if (lane == 31) r = fmaf(fbs[kChroma * 32 * 32 + c], p512, r);
