@@ -151,16 +151,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // warp-uniform but only known at run time, so the steps are fully unrolled behind a switch with
 // fall-through (one indirect branch per group instead of a counted loop: the loop control used to
 // cost as many issue slots as the multiply-adds).
-#define HLMC_MEL_STEP(S)                                        \
-    {                                                           \
-        const float4 w = wp[32 * (S)];                          \
-        a0 = fmaf(w.x, pp[4 * (S) + 0], a0);                    \
-        a1 = fmaf(w.y, pp[4 * (S) + 1], a1);                    \
-        a2 = fmaf(w.z, pp[4 * (S) + 2], a2);                    \
-        a3 = fmaf(w.w, pp[4 * (S) + 3], a3);                    \
+#define HLMC_MEL_STEP(S)                                                                         \
+    {                                                                                            \
+        const float4 w = wp[32 * (S)];                                                           \
+        a01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(pp[4 * (S) + 0], pp[4 * (S) + 1]), a01); \
+        a23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(pp[4 * (S) + 2], pp[4 * (S) + 3]), a23); \
     }
 __device__ __forceinline__ void mel_steps(int n4, const float4* __restrict__ wp, const float* __restrict__ pp,
-                                          float& a0, float& a1, float& a2, float& a3) {
+                                          float2& a01, float2& a23) {
     for (; n4 > 16; --n4) HLMC_MEL_STEP(n4 - 1)
     switch (n4) {
         case 16: HLMC_MEL_STEP(15)
@@ -326,10 +324,9 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
         const float2 e = __fadd2_rn(za_, make_float2(zb_.x, -zb_.y));      // Z[k] + conj Z[1024-k]
         const float2 d = __fadd2_rn(za_, make_float2(-zb_.x, zb_.y));      // Z[k] - conj Z[1024-k]
         const float2 tt = fftreg2::cmul(d, tw.x, tw.y);
-        // X[k] = e + t, conj X[1024-k] = e - t; pair the real parts and the imaginary parts
-        const float2 R = __fadd2_rn(make_float2(e.x, e.x), make_float2(tt.x, -tt.x));
-        const float2 I = __fadd2_rn(make_float2(e.y, e.y), make_float2(tt.y, -tt.y));
-        const float2 pw = __ffma2_rn(R, R, __fmul2_rn(I, I));              // (|X[k]|^2, |X[1024-k]|^2)
+        // X[k] = e + t, conj X[1024-k] = e - t (both carry the 1/2 folded into the window)
+        const float2 xa = __fadd2_rn(e, tt), xb = __fadd2_rn(e, make_float2(-tt.x, -tt.y));
+        const float2 pw = make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
         const float2 sq = make_float2(fast_sqrt(pw.x), fast_sqrt(pw.y));
         P[i] = pw;
         S[i] = sq;
@@ -538,10 +535,10 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 const int n4 = s_meta[g];
                 const float4* wp = reinterpret_cast<const float4*>(s_melw + s_meta[kMaxMelGroups + g]) + lane;
                 const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * g + lane];
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                mel_steps(n4, wp, pp, a0, a1, a2, a3);
-                a0 += a2; a1 += a3;
-                const float acc = a0 + a1;
+                float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
+                mel_steps(n4, wp, pp, a01, a23);
+                a01 = __fadd2_rn(a01, a23);
+                const float acc = a01.x + a01.y;
                 const int m = 32 * g + lane;
                 if (m < a.n_mels) outb[(size_t)m * mstride] = acc;
                 wmax = fmaxf(wmax, acc);
@@ -1384,7 +1381,7 @@ constexpr int kDbThreads = 128;
 __host__ __device__ constexpr int db_frames(int nc) { return nc <= 40 ? 2 : 1; }
 
 template <int NC>
-__global__ void __launch_bounds__(kDbThreads, (NC <= 40) ? 4 : 1) db_dct(const DbArgs a) {
+__global__ void __launch_bounds__(kDbThreads, (NC <= 32) ? 4 : (NC <= 40) ? 3 : 1) db_dct(const DbArgs a) {
     // The DCT-II basis is symmetric (even k) / antisymmetric (odd k) about the middle of the mel axis:
     // cos(pi (2(N-1-n)+1) k / 2N) = (-1)^k cos(pi (2n+1) k / 2N).  Folding the input into
     // s_n = x_n + x_(N-1-n) and d_n = x_n - x_(N-1-n) halves the multiply-adds: even coefficients
@@ -1429,11 +1426,12 @@ __global__ void __launch_bounds__(kDbThreads, (NC <= 40) ? 4 : 1) db_dct(const D
         mfcc_off[f] = (size_t)b * a.n_mfcc * a.T + t;
     }
     if (!live[0]) return;
-    float acc[F][NC > 0 ? NC : 1];
+    // packed FP32 pairs: acc[f][j] holds sD columns 2j and 2j + 1 (j < H/2: even coefficients, else odd ones)
+    float2 acc[F][NC > 0 ? H : 1];
 #pragma unroll
     for (int f = 0; f < F; ++f)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[f][c] = 0.0f;
+        for (int c = 0; c < H; ++c) acc[f][c] = make_float2(0.0f, 0.0f);
     const bool vec = (a.mel_in != nullptr) && ((a.n_mels & 7) == 0);
     // one mel row: dB for the log-mel output, the (ref = 1, top_db = 80) dB value for the DCT
     auto to_db = [&](int f, float p, int m) -> float {
@@ -1478,15 +1476,12 @@ __global__ void __launch_bounds__(kDbThreads, (NC <= 40) ? 4 : 1) db_dct(const D
                 for (int c = 0; c < H / 4; ++c) {
                     const float4 e = d4[c], o = d4[H / 4 + c];
 #pragma unroll
-                    for (int f = 0; f < F; ++f) {
-                        acc[f][4 * c + 0] = fmaf(e.x, s[f], acc[f][4 * c + 0]);
-                        acc[f][4 * c + 1] = fmaf(e.y, s[f], acc[f][4 * c + 1]);
-                        acc[f][4 * c + 2] = fmaf(e.z, s[f], acc[f][4 * c + 2]);
-                        acc[f][4 * c + 3] = fmaf(e.w, s[f], acc[f][4 * c + 3]);
-                        acc[f][H + 4 * c + 0] = fmaf(o.x, d[f], acc[f][H + 4 * c + 0]);
-                        acc[f][H + 4 * c + 1] = fmaf(o.y, d[f], acc[f][H + 4 * c + 1]);
-                        acc[f][H + 4 * c + 2] = fmaf(o.z, d[f], acc[f][H + 4 * c + 2]);
-                        acc[f][H + 4 * c + 3] = fmaf(o.w, d[f], acc[f][H + 4 * c + 3]);
+                    for (int f = 0; f < F; ++f) {       // packed FP32: two coefficients per FFMA2
+                        const float2 sf = make_float2(s[f], s[f]), df = make_float2(d[f], d[f]);
+                        acc[f][2 * c] = __ffma2_rn(make_float2(e.x, e.y), sf, acc[f][2 * c]);
+                        acc[f][2 * c + 1] = __ffma2_rn(make_float2(e.z, e.w), sf, acc[f][2 * c + 1]);
+                        acc[f][H / 2 + 2 * c] = __ffma2_rn(make_float2(o.x, o.y), df, acc[f][H / 2 + 2 * c]);
+                        acc[f][H / 2 + 2 * c + 1] = __ffma2_rn(make_float2(o.z, o.w), df, acc[f][H / 2 + 2 * c + 1]);
                     }
                 }
             }
@@ -1498,7 +1493,9 @@ __global__ void __launch_bounds__(kDbThreads, (NC <= 40) ? 4 : 1) db_dct(const D
             const float x = to_db(f, fetch(f, half), half);
             if constexpr (NC > 0) {
 #pragma unroll
-                for (int c = 0; c < H; ++c) acc[f][c] = fmaf(sD[half * NC + c], x, acc[f][c]);
+                for (int c = 0; c < H / 2; ++c)
+                    acc[f][c] = __ffma2_rn(make_float2(sD[half * NC + 2 * c], sD[half * NC + 2 * c + 1]),
+                                           make_float2(x, x), acc[f][c]);
             }
         }
     }
@@ -1508,9 +1505,11 @@ __global__ void __launch_bounds__(kDbThreads, (NC <= 40) ? 4 : 1) db_dct(const D
             if (!live[f]) continue;
             float* mo = a.mfcc + mfcc_off[f];
 #pragma unroll
-            for (int j = 0; j < H; ++j) {
-                if (2 * j < a.n_mfcc) mo[(size_t)(2 * j) * a.T] = acc[f][j];
-                if (2 * j + 1 < a.n_mfcc) mo[(size_t)(2 * j + 1) * a.T] = acc[f][H + j];
+            for (int j = 0; j < H; ++j) {       // sD column j = coefficient 2j, column H + j = coefficient 2j + 1
+                const float ev = (j & 1) ? acc[f][j >> 1].y : acc[f][j >> 1].x;
+                const float od = (j & 1) ? acc[f][H / 2 + (j >> 1)].y : acc[f][H / 2 + (j >> 1)].x;
+                if (2 * j < a.n_mfcc) mo[(size_t)(2 * j) * a.T] = ev;
+                if (2 * j + 1 < a.n_mfcc) mo[(size_t)(2 * j + 1) * a.T] = od;
             }
         }
     }
