@@ -412,12 +412,18 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
             }
         }
         auto r4 = [](int x) { return (x + 3) & ~3; };
-        ft.win = 0;
-        ft.tw1 = ft.win + N;
+        ft.tw1 = 0;
         ft.tw2 = ft.tw1 + 31 * 32 * 2;
-        ft.mel_meta = ft.tw2 + 16 * 32 * 2;
+        ft.hann_cs = ft.tw2 + 32 * 2;
+        ft.mel_meta = ft.hann_cs + 32 * 4;
         ft.mel_w = r4(ft.mel_meta + (int)meta.size());
-        ft.total = r4(ft.mel_w + (int)melw.size());
+        ft.nowin = r4(ft.mel_w + (int)melw.size());
+        ft.win = ft.nowin;
+        ft.total = ft.win + N;
+        // full-length periodic Hann (the default): the kernel may synthesise the window from 4 values per lane
+        ft.hann = (p.win_length == N) ? 1 : 0;
+        for (int i = 0; window && ft.hann && i < N; ++i)          // a caller-supplied window counts if it IS that Hann
+            if (fabs(window[i] - (0.5 - 0.5 * cos(2.0 * M_PI * double(i) / double(N)))) > 1e-9) ft.hann = 0;
         ft.scr = r4(kReadEnd + 3);
         std::vector<float> blob(ft.total, 0.0f);
         memcpy(&blob[ft.win], win.data(), N * 4);
@@ -427,12 +433,16 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
                 blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 0] = float(cos(th));
                 blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 1] = float(-sin(th));
             }
-        for (int i = 0; i < 16; ++i)
-            for (int l = 0; l < 32; ++l) {
-                const double th = 2.0 * M_PI * double(16 * l + i) / 2048.0;
-                blob[ft.tw2 + (i * 32 + l) * 2 + 0] = float(-sin(th));
-                blob[ft.tw2 + (i * 32 + l) * 2 + 1] = float(-cos(th));
-            }
+        for (int l = 0; l < 32; ++l) {
+            const double th = 2.0 * M_PI * double(16 * l) / 2048.0;           // -i * W_2048^(16 l)
+            blob[ft.tw2 + l * 2 + 0] = float(-sin(th));
+            blob[ft.tw2 + l * 2 + 1] = float(-cos(th));
+            const double te = 2.0 * M_PI * double(2 * l) / double(N), to = 2.0 * M_PI * double(2 * l + 1) / double(N);
+            blob[ft.hann_cs + 4 * l + 0] = float(cos(te));
+            blob[ft.hann_cs + 4 * l + 1] = float(cos(to));
+            blob[ft.hann_cs + 4 * l + 2] = float(sin(te));
+            blob[ft.hann_cs + 4 * l + 3] = float(sin(to));
+        }
         memcpy(&blob[ft.mel_meta], meta.data(), meta.size() * 4);
         if (!melw.empty()) memcpy(&blob[ft.mel_w], melw.data(), melw.size() * 4);
         pl->ft = ft;

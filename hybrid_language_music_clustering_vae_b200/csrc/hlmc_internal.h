@@ -9,16 +9,21 @@ namespace hlmc {
 constexpr int kMaxMelGroups = 8;     // n_mels <= 256
 constexpr int kFastNfft = 2048;      // the register-FFT path is specialised for this size
 
-// Layout (in floats) of the table blob the fast kernel stages into shared memory.
+// Layout (in floats) of the table blob the fast kernel stages into shared memory.  For n_fft = 2048
+// the window comes last so that kernels which synthesise it stage only the first `nowin` floats.
 struct FastTables {
     int win;        // n_fft floats: 0.5 * window (the real-FFT split's 1/2 is folded in)
     int tw1;        // 31*32 float2: W_1024^(lane*k1), k1 = 1..31
-    int tw2;        // 17*32 float2: -i * W_2048^(16*lane + i), i = 0..15; row 16 = bin 512
+    int tw2;        // n_fft 2048: 32 float2, -i * W_2048^(16*lane) (the kernel rotates it to bins 16*lane + i);
+                    // n_fft 1024 / 512: 16*L float2, -i * W_n_fft^(16*lane + i)
     int mel_meta;   // int32: gmax[8], goff[8], qlo[32*n_groups]
     int mel_w;      // floats: per group, [i][lane] weights (zero padded to gmax)
     int total;      // floats, multiple of 4
     int n_groups;
     int scr;        // per-warp scratch floats (>= 1089 + max gmax, multiple of 4)
+    int hann;       // 1: the window is the full-length periodic Hann (n_fft 2048: synthesised in registers)
+    int hann_cs;    // 32 float4: (cos, cos', sin, sin') of 2*pi*(2*lane + {0,1}) / n_fft
+    int nowin;      // floats before the window (multiple of 4)
 };
 
 struct FrameArgs {

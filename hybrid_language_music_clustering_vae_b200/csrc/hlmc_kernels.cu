@@ -120,21 +120,30 @@ constexpr int kWarpBufFloats4 = (kWarpBufFloats + 3) & ~3;   // padded 1024-bin 
 
 __host__ __device__ constexpr int pos32(int k) { return fftreg::fft_pos<32>(k); }
 
+// PREF kernels keep the TMA landing zone apart from the scratch of the last phases, so that the next
+// frame's samples can be in flight while this frame finishes: [0, kLandOff) power-spectrum scratch,
+// [kLandOff, kLandOff + 2048 + 4) landing zone; the transposes run over [0, 2180) once the samples are
+// in registers.
+constexpr int kLandOff = 1108;
+constexpr int kPrefBufFloats = kLandOff + kFastNfft + 4;
+
 struct FastSmemLayout {
-    int bars, tables, wbuf, wb, total;   // float offsets; wb = floats per warp buffer
+    int bars, tables, ntab, wbuf, wb, total;   // float offsets; ntab = table floats staged; wb = floats per warp buffer
 };
-__host__ __device__ inline FastSmemLayout fast_layout(const FastTables& ft, int nw) {
+__host__ __device__ inline FastSmemLayout fast_layout(const FastTables& ft, int nw, bool pref) {
     FastSmemLayout L;
     L.bars = 0;                                   // nw mbarriers, 8 B each
     L.tables = (2 * nw + 3) & ~3;
-    L.wbuf = L.tables + ft.total;
-    L.wb = (((ft.scr > kWarpBufFloats) ? ft.scr : kWarpBufFloats) + 3) & ~3;
+    L.ntab = pref ? ft.nowin : ft.total;          // PREF kernels synthesise the Hann window: no table
+    L.wbuf = L.tables + L.ntab;
+    const int scr = (ft.scr > kWarpBufFloats) ? ft.scr : kWarpBufFloats;
+    L.wb = pref ? kPrefBufFloats : ((scr + 3) & ~3);
     L.total = L.wbuf + nw * L.wb;
     return L;
 }
 int fast_smem_bytes(const FastTables& ft, int nwarps, int n_fft, int hop, int n_mels) {
     (void)n_fft; (void)hop; (void)n_mels;
-    return fast_layout(ft, nwarps).total * 4;
+    return fast_layout(ft, nwarps, false).total * 4;
 }
 int pick_fast_warps(int T) { (void)T; return 16; }
 
@@ -148,37 +157,31 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // Banded mel gather of one (group, lane): n4 float4 steps of 4 taps each.  The step count is
-// warp-uniform but only known at run time, so the steps are fully unrolled behind a switch with
-// fall-through (one indirect branch per group instead of a counted loop: the loop control used to
-// cost as many issue slots as the multiply-adds).
-#define HLMC_MEL_STEP(S)                                                                         \
-    {                                                                                            \
-        const float4 w = wp[32 * (S)];                                                           \
-        a01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(pp[4 * (S) + 0], pp[4 * (S) + 1]), a01); \
-        a23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(pp[4 * (S) + 2], pp[4 * (S) + 3]), a23); \
+// warp-uniform but only known at run time.  Steps are taken in straight-line chunks of 4, 2 and 1 so
+// that all shared-memory loads of a chunk are in flight before its first multiply-add (a step-by-step
+// loop pays the full load latency 26 times per frame; ncu showed it as the top short-scoreboard stall).
+template <int CH>
+__device__ __forceinline__ void mel_chunk(const float4* __restrict__ wp, const float* __restrict__ pp,
+                                          float2& a01, float2& a23) {
+    float4 w[CH];
+    float2 p01[CH], p23[CH];
+#pragma unroll
+    for (int s = 0; s < CH; ++s) {
+        w[s] = wp[32 * s];
+        p01[s] = make_float2(pp[4 * s + 0], pp[4 * s + 1]);
+        p23[s] = make_float2(pp[4 * s + 2], pp[4 * s + 3]);
     }
+#pragma unroll
+    for (int s = 0; s < CH; ++s) {
+        a01 = __ffma2_rn(make_float2(w[s].x, w[s].y), p01[s], a01);
+        a23 = __ffma2_rn(make_float2(w[s].z, w[s].w), p23[s], a23);
+    }
+}
 __device__ __forceinline__ void mel_steps(int n4, const float4* __restrict__ wp, const float* __restrict__ pp,
                                           float2& a01, float2& a23) {
-    for (; n4 > 16; --n4) HLMC_MEL_STEP(n4 - 1)
-    switch (n4) {
-        case 16: HLMC_MEL_STEP(15)
-        case 15: HLMC_MEL_STEP(14)
-        case 14: HLMC_MEL_STEP(13)
-        case 13: HLMC_MEL_STEP(12)
-        case 12: HLMC_MEL_STEP(11)
-        case 11: HLMC_MEL_STEP(10)
-        case 10: HLMC_MEL_STEP(9)
-        case 9: HLMC_MEL_STEP(8)
-        case 8: HLMC_MEL_STEP(7)
-        case 7: HLMC_MEL_STEP(6)
-        case 6: HLMC_MEL_STEP(5)
-        case 5: HLMC_MEL_STEP(4)
-        case 4: HLMC_MEL_STEP(3)
-        case 3: HLMC_MEL_STEP(2)
-        case 2: HLMC_MEL_STEP(1)
-        case 1: HLMC_MEL_STEP(0)
-        default: break;
-    }
+    for (; n4 >= 4; n4 -= 4, wp += 4 * 32, pp += 16) mel_chunk<4>(wp, pp, a01, a23);
+    if (n4 & 2) { mel_chunk<2>(wp, pp, a01, a23); wp += 2 * 32; pp += 8; }
+    if (n4 & 1) mel_chunk<1>(wp, pp, a01, a23);
 }
 
 struct WarpState {
@@ -187,8 +190,33 @@ struct WarpState {
     uint64_t* mbar;
     uint32_t parity;
     const float2 *s_win, *s_tw1, *s_tw2;
+    const float4* s_hcs;       // per-lane (cos, cos', sin, sin') of the Hann phase (PREF kernels)
     int lane, zw_base, zlo_base, zhi_base, zhi0;
+    bool pending;              // a TMA copy of the next frame to process is in flight (PREF kernels)
+    int pend_off;              // its alignment shift
 };
+
+// Start the TMA bulk copy of frame t of `clip` into `land` if the frame holds no padding and is 8-byte
+// aligned (16-byte aligned source, 0..3 leading floats).  Returns the shift, or -1 if the frame has to be
+// built by hand.
+__device__ __forceinline__ int issue_frame_tma(const FrameArgs& a, const WarpState& w, float* land,
+                                               const float* clip, int t) {
+    const int fs = t * a.hop - a.pad;
+    const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
+    const int shift = (int)((addr & 15) >> 2);
+    if (!interior || (shift & 1)) return -1;
+    if (w.lane == 0) {
+        const float* src0 = reinterpret_cast<const float*>(addr & ~uintptr_t(15));
+        const int tot = shift + kFastNfft;
+        const int bulk = tot & ~3;
+        for (int i = bulk; i < tot; ++i) land[i] = __ldg(src0 + i);     // <= 3 tail floats
+        fence_proxy_async_smem();       // order earlier generic accesses before the async write
+        mbar_arrive_expect_tx(w.mbar, (uint32_t)bulk * 4u);
+        tma_bulk_g2s(land, src0, (uint32_t)bulk * 4u, w.mbar);
+    }
+    return shift;
+}
 
 // One frame, from samples to spectrum, shared by the feature kernel and the chroma kernel.
 // On return P[i] / S[i] hold |X|^2 / |X| of bin 16*lane + i (.x, the lane's low run) and of bin
@@ -196,7 +224,16 @@ struct WarpState {
 // the frame's samples, zc = zero crossings; m0*/m1*/m2* are the lane's magnitude moments (orders
 // 0-2) about the centres of its two 16-bin runs.
 // All complex arithmetic is packed FP32 (FADD2 / FMUL2 / FFMA2): one float2 = (re, im).
+//
+// PREF (full-length periodic Hann window only): (1) the window is not read from shared memory but
+// synthesised, 0.5*w[2(lane+32j)+c] = 0.25 - 0.25 cos(theta_lane,c + 2 pi j / 32), expanded with the
+// angle-addition formula into two FFMA2 on per-lane (cos, sin) pairs and immediates; the 8 KB this
+// frees pay for (2) a landing zone of its own, so the TMA copy of the warp's NEXT frame (nclip, nt) is
+// started as soon as the transposes are done and flies while the statistics and the mel projection of
+// this frame run - the wait at the top of the next frame is then (nearly) free.
+template <bool PREF>
 __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
+                                               const float* nclip, int nt,
                                                float2 (&P)[16], float2 (&S)[16], float& p512, float& s512,
                                                float& ss, int& zc, float& m0l, float& m1l, float& m2l,
                                                float& m0h, float& m1h, float& m2h) {
@@ -210,37 +247,39 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     const float zthr = a.zcr_thr;
     uint32_t& parity = w.parity;
     const int fs = t * a.hop - a.pad;              // first sample of the frame (clip coords)
-    const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
-    const int shift = (int)((addr & 15) >> 2);
+    float* const land = PREF ? sc + kLandOff : sc; // where the frame's samples are staged
     int zc_edge = -1;
     int off;
 
     // ---- stage the frame's samples in this warp's buffer
-    if (interior && !(shift & 1)) {
-        if (lane == 0) {
-            const float* src0 = reinterpret_cast<const float*>(addr & ~uintptr_t(15));
-            const int tot = shift + kFastNfft;
-            const int bulk = tot & ~3;
-            for (int i = bulk; i < tot; ++i) sc[i] = __ldg(src0 + i);     // <= 3 tail floats
-            fence_proxy_async_smem();       // order earlier generic accesses before the async write
-            mbar_arrive_expect_tx(mbar, (uint32_t)bulk * 4u);
-            tma_bulk_g2s(sc, src0, (uint32_t)bulk * 4u, mbar);
-        }
+    if (!PREF || !w.pending) off = issue_frame_tma(a, w, land, clip, t);
+    else off = w.pend_off;
+    w.pending = false;
+    if (off >= 0) {
         mbar_wait(mbar, parity);
         parity ^= 1u;
-        off = shift;
     } else {
         // edge frame (or odd alignment): build the padded frame by hand; ZCR pads with "edge"
         int zc = 0;
         unsigned prev_last = 0u;
-        for (int c = 0; c < kFastNfft / 32; ++c) {
-            const int s = fs + 32 * c + lane;
-            sc[32 * c + lane] = sample_padded(clip, a.n, s, a.pad_mode);
-            const unsigned msk = __ballot_sync(FULL, sample_edge(clip, a.n, s) < -zthr);
-            zc += __popc((msk ^ (msk >> 1)) & 0x7fffffffu);
-            if (c > 0) zc += ((msk & 1u) != prev_last) ? 1 : 0;
-            prev_last = msk >> 31;
+        for (int c0 = 0; c0 < kFastNfft / 32; c0 += 8) {
+            float ve[8], vp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ve[u] = sample_edge(clip, a.n, fs + 32 * (c0 + u) + lane);   // 8 loads in flight
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int s = fs + 32 * (c0 + u) + lane;
+                const bool inside = (s >= 0) && (s < a.n);
+                vp[u] = inside ? ve[u] : ((a.pad_mode == 0) ? 0.0f : (a.pad_mode == 1) ? __ldg(clip + reflect_index(s, a.n)) : ve[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                land[32 * (c0 + u) + lane] = vp[u];
+                const unsigned msk = __ballot_sync(FULL, ve[u] < -zthr);
+                zc += __popc((msk ^ (msk >> 1)) & 0x7fffffffu);
+                if (c0 + u > 0) zc += ((msk & 1u) != prev_last) ? 1 : 0;
+                prev_last = msk >> 31;
+            }
         }
         zc_edge = zc;
         off = 0;
@@ -252,13 +291,25 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
 
     // ---- phase 0: frame -> registers; window; RMS and ZCR partials
     {
-        const float2* xp = reinterpret_cast<const float2*>(sc + off);
+        const float2* xp = reinterpret_cast<const float2*>(land + off);
         const float2 zt = make_float2(zthr, zthr);
         float2 ss2 = make_float2(0.0f, 0.0f);
+        float2 hc = make_float2(0.f, 0.f), hs = hc;
+        if (PREF) { const float4 cs = w.s_hcs[lane]; hc = make_float2(cs.x, cs.y); hs = make_float2(cs.z, cs.w); }
+        const float2 quarter = make_float2(0.25f, 0.25f);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const float2 x = xp[lane + 32 * j];
-            const float2 wn = s_win[lane + 32 * j];
+            float2 wn;
+            if (PREF) {
+                // 0.25 - 0.25 cos(theta) cos(phi_j) + 0.25 sin(theta) sin(phi_j), phi_j = 2 pi j / 32
+                const float cj = -0.25f * float(fftreg::cos2pi(j, 32)), sj = 0.25f * float(fftreg::sin2pi(j, 32));
+                if (j == 0 || j == 16) wn = __ffma2_rn(hc, make_float2(cj, cj), quarter);
+                else if (j == 8 || j == 24) wn = __ffma2_rn(hs, make_float2(sj, sj), quarter);
+                else wn = __ffma2_rn(hc, make_float2(cj, cj), __ffma2_rn(hs, make_float2(sj, sj), quarter));
+            } else {
+                wn = s_win[lane + 32 * j];
+            }
             ss2 = __ffma2_rn(x, x, ss2);
             // sign bit of (x + thr) <=> x < -thr; sample j ends up at bit 31 - j
             const float2 xt = __fadd2_rn(x, zt);
@@ -315,11 +366,20 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     const float2 e512 = sc2[544];
     __syncwarp();
 
+    // ---- the landing zone is free again: start the copy of this warp's next frame
+    if (PREF && nclip != nullptr) {
+        const int sh = issue_frame_tma(a, w, land, nclip, nt);
+        w.pending = sh >= 0;
+        w.pend_off = sh;
+    }
+
     // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
     float2 M0 = make_float2(0.f, 0.f), M1 = M0, M2 = M0;
+    const float2 tw_base = s_tw2[lane];            // -i * W_2048^(16*lane); bin 16*lane + i needs it times W_2048^i
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const float2 tw = s_tw2[i * 32 + lane];
+        const float2 tw = (i == 0) ? tw_base
+                                   : fftreg2::cmul_conj(tw_base, float(fftreg::cos2pi(i, 2048)), float(fftreg::sin2pi(i, 2048)));
         const float2 za_ = v[i], zb_ = v[16 + i];
         const float2 e = __fadd2_rn(za_, make_float2(zb_.x, -zb_.y));      // Z[k] + conj Z[1024-k]
         const float2 d = __fadd2_rn(za_, make_float2(-zb_.x, zb_.y));      // Z[k] - conj Z[1024-k]
@@ -341,17 +401,17 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     s512 = fast_sqrt(p512);
 }
 
-template <int NW, bool PIP>
+template <int NW, bool PIP, bool PREF>
 __global__ void __launch_bounds__(NW * 32, 1)
 frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const FastSmemLayout L = fast_layout(ft, NW);
+    const FastSmemLayout L = fast_layout(ft, NW, PREF);
 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
     float* tab = smem + L.tables;
-    const float2* s_win = reinterpret_cast<const float2*>(tab + ft.win);
+    const float2* s_win = reinterpret_cast<const float2*>(tab + ft.win);   // (not staged by PREF kernels)
     const float2* s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + ft.tw2);
     const int* s_meta = reinterpret_cast<const int*>(tab + ft.mel_meta);
@@ -360,7 +420,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     float2* sc2 = reinterpret_cast<float2*>(sc);
 
     // ---- one-time CTA setup: tables -> smem, zero the warp buffers, one mbarrier per warp
-    for (int i = tid; i < ft.total / 4; i += NT)
+    for (int i = tid; i < L.ntab / 4; i += NT)
         reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
     for (int i = L.wbuf + tid; i < L.total; i += NT) smem[i] = 0.0f;
     if (lane == 0) {
@@ -384,6 +444,8 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     WarpState w;
     w.sc = sc; w.sc2 = sc2; w.mbar = mbar; w.parity = 0;
     w.s_win = s_win; w.s_tw1 = s_tw1; w.s_tw2 = s_tw2; w.lane = lane;
+    w.s_hcs = reinterpret_cast<const float4*>(tab + ft.hann_cs);
+    w.pending = false; w.pend_off = 0;
     // per-lane bases of the regroup buffer, layout p(k) = k + k/16 in float2 units: every
     // access is base + immediate and conflict-free (17 is odd)
     w.zw_base = lane + (lane >> 4);              // write: k = lane + 32*k2 -> zw_base + 34*k2
@@ -393,10 +455,14 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
 
     for (long long g = g0; g < g1; g += NW) {
         const float* clip = a.wave + (long long)b * a.pitch;
+        // this warp's next frame (PREF kernels start its copy half-way through this one)
+        int nb = b, nt = t + NW;
+        while (nt >= a.T) { nt -= a.T; ++nb; }
+        const float* nclip = (PREF && g + NW < g1) ? a.wave + (long long)nb * a.pitch : nullptr;
         float2 P[16], S[16];
         float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
         int zc;
-        frame_spectrum(a, w, clip, t, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
+        frame_spectrum<PREF>(a, w, clip, t, nclip, nt, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
 
         // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
         const float kcl = 16.0f * lane + 7.5f;
@@ -564,24 +630,23 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             if (lane == 0) atomicMax(reinterpret_cast<int*>(a.clipmax) + b, __float_as_int(m));
             clip_max = 0.0f;
         }
-        t += NW;
-        while (t >= a.T) { t -= a.T; ++b; }
+        t = nt; b = nb;
         __syncwarp();                       // scratch reads are done before the next frame lands
     }
 }
 
-template <int NW, bool PIP>
+template <int NW, bool PIP, bool PREF>
 static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                   int num_sms, cudaStream_t stream) {
-    const int smem = fast_smem_bytes(ft, NW, a.n_fft, a.hop, a.n_mels);
-    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP>,
+    const int smem = fast_layout(ft, NW, PREF).total * 4;
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP, PREF>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long frames = (long long)a.B * a.T;
     if (frames <= 0) return cudaSuccess;
     long long grid = (frames + NW - 1) / NW;
     if (grid > num_sms) grid = num_sms;
-    frames_fast_2048<NW, PIP><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    frames_fast_2048<NW, PIP, PREF><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
@@ -589,12 +654,18 @@ static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, con
 cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                int num_sms, cudaStream_t stream) {
     const bool pip = (a.cand != nullptr);
-    if (fast_smem_bytes(ft, 16, a.n_fft, a.hop, a.n_mels) <= 227 * 1024)
-        return pip ? launch_fast_nw<16, true>(a, d_tables, ft, num_sms, stream)
-                   : launch_fast_nw<16, false>(a, d_tables, ft, num_sms, stream);
-    if (fast_smem_bytes(ft, 8, a.n_fft, a.hop, a.n_mels) <= 227 * 1024)
-        return pip ? launch_fast_nw<8, true>(a, d_tables, ft, num_sms, stream)
-                   : launch_fast_nw<8, false>(a, d_tables, ft, num_sms, stream);
+    constexpr int kMaxSmem = 227 * 1024;
+    // default window: 16 warps with the next frame's copy in flight (Hann synthesised in registers)
+    static const bool no_pref = [] { const char* e = getenv("HLMC_NO_PREF"); return e && e[0] == '1'; }();
+    if (!no_pref && ft.hann && fast_layout(ft, 16, true).total * 4 <= kMaxSmem)
+        return pip ? launch_fast_nw<16, true, true>(a, d_tables, ft, num_sms, stream)
+                   : launch_fast_nw<16, false, true>(a, d_tables, ft, num_sms, stream);
+    if (fast_layout(ft, 16, false).total * 4 <= kMaxSmem)
+        return pip ? launch_fast_nw<16, true, false>(a, d_tables, ft, num_sms, stream)
+                   : launch_fast_nw<16, false, false>(a, d_tables, ft, num_sms, stream);
+    if (fast_layout(ft, 8, false).total * 4 <= kMaxSmem)
+        return pip ? launch_fast_nw<8, true, false>(a, d_tables, ft, num_sms, stream)
+                   : launch_fast_nw<8, false, false>(a, d_tables, ft, num_sms, stream);
     return cudaErrorInvalidValue;
 }
 
@@ -1130,7 +1201,7 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ntab = ft.mel_meta;                      // window + both twiddle tables only
+    const int ntab = ft.total;                         // the whole table blob (twiddles ... window)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
     float* tab = smem + ((2 * NW + 3) & ~3);
     float* fbs = tab + ntab;                           // this clip's filterbank
@@ -1146,6 +1217,7 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
     w.s_win = reinterpret_cast<const float2*>(tab + ft.win);
     w.s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
     w.s_tw2 = reinterpret_cast<const float2*>(tab + ft.tw2);
+    w.s_hcs = nullptr; w.pending = false; w.pend_off = 0;
     w.lane = lane;
     w.zw_base = lane + (lane >> 4);
     w.zlo_base = 17 * lane;
@@ -1162,7 +1234,7 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
             float2 P[16], S[16];
             float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
             int zc;
-            frame_spectrum(a, w, clip, t, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
+            frame_spectrum<false>(a, w, clip, t, nullptr, 0, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
             // filterbank column j of this lane: j < 16 -> bin 16*lane + j, else bin 1024 - 16*lane - (j - 16)
             auto pw = [&](int j) -> float { return j < 16 ? P[j].x : P[j - 16].y; };
             float raw[kChroma];
@@ -1199,7 +1271,7 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
 cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,
                                const FastTables& ft, int num_sms, cudaStream_t stream) {
     constexpr int NW = 16;
-    const int smem = (((2 * NW + 3) & ~3) + ft.mel_meta + kChromaFbFloats + NW * kWarpBufFloats4) * 4;
+    const int smem = (((2 * NW + 3) & ~3) + ft.total + kChromaFbFloats + NW * kWarpBufFloats4) * 4;
     cudaError_t e = cudaFuncSetAttribute(chroma_fast_2048<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     if (a.B <= 0) return cudaSuccess;
