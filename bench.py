@@ -203,6 +203,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one rank per GPU: keep the rank's pinned buffers on the GPU's own NUMA node
+    numa_bound = hl.sharding.bind_to_gpu_numa_node(local_rank) if world > 1 else False
     if world > 1:
         # NCCL prints its version banner on the C-level stdout at the first collective; keep
         # stdout clean for the single JSON line by pointing fd 1 at stderr while it initialises
@@ -369,7 +371,7 @@ def main():
     }
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:       # the CPU baseline is reported at N = 1 only
         for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ.setdefault(k, "1")
         cores = host_cores()
@@ -387,7 +389,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "clips_per_gpu": B, "samples_per_clip": n, "frames_per_clip": T,
                    "chroma_stft_included": bool(args.chroma),
-                   "l2_policy": "inputs larger than L2 (2.6 GB per step)", "parallelism": f"clips sharded x{world}, no collective"},
+                   "l2_policy": "inputs larger than L2 (2.6 GB per step)", "parallelism": f"clips sharded x{world}, no collective",
+                   "numa_bound": bool(numa_bound)},
         "audio_hours_per_sec": value * args.seconds / 3600.0,
         "e2e": e2e, "e2e_pcm16": e2e_pcm, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "nonfinite_clips": status_bad,

@@ -7,6 +7,7 @@ or plain slice writes across threads in ``extract_multi_gpu``).
 """
 from __future__ import annotations
 
+import os
 import threading
 
 import numpy as np
@@ -18,6 +19,56 @@ def shard_bounds(B: int, rank: int, world: int):
     lo = min(B, rank * per)
     hi = min(B, lo + per)
     return lo, hi
+
+
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def gpu_numa_cpus(device: int):
+    """CPUs of the NUMA node the GPU `device` hangs off (sysfs), or None if unknown."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        return cpus or None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device: int) -> bool:
+    """Pin the calling process to the CPUs next to GPU `device` BEFORE it allocates pinned host
+    buffers, so that first-touch places them on the GPU's NUMA node: with 8 ranks on a two-socket
+    box the H2D / D2H copies otherwise cross the socket link for half of the GPUs.  Returns True
+    if the affinity was changed.  No collective, no effect on results."""
+    cpus = gpu_numa_cpus(device)
+    if not cpus:
+        return False
+    try:
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        if not target or target == allowed:
+            return False
+        os.sched_setaffinity(0, target)
+        return True
+    except Exception:
+        return False
 
 
 def gather_host(local: np.ndarray, B: int, rank: int, world: int, group=None, dst: int = 0):
