@@ -49,6 +49,7 @@ struct hlmc_plan {
     int ncp = 0;
     // device tables
     float* d_fast = nullptr; FastTables ft{};
+    float* d_fast4 = nullptr; Fast4Tables ft4{}; bool fast4_ok = false;   // n_fft = 4096 register-FFT kernel
     float* d_win = nullptr; float2* d_twm = nullptr; float2* d_tws = nullptr;
     int* d_mel_lo = nullptr; int* d_mel_len = nullptr; int* d_mel_off = nullptr; float* d_mel_w = nullptr;
     float* d_dct_t = nullptr;
@@ -124,6 +125,97 @@ static int validate(const hlmc_params& p) {
     if (p.zcr_threshold < 0.0f) return fail(HLMC_ERR_PARAM, "zero-crossing threshold must be non-negative");
     if (p.ref_mode != HLMC_REF_VALUE && p.ref_mode != HLMC_REF_MAX) return fail(HLMC_ERR_PARAM, "bad ref_mode");
     return HLMC_OK;
+}
+
+// Banded layout of a dense (nm x F) filterbank for the register-FFT kernels' mel gather: filters in groups
+// of 32 (one per lane), each group padded to a common number of float4 steps, every lane's first tap
+// shifted so that the 32 lanes start on 32 different shared-memory banks.  meta: [0..7] float4 steps per
+// group, [8..15] weight offset per group, then the (shifted) first tap of every (group, lane) in the
+// padded spectrum layout q(k) = k + k/16.
+static void build_banded_groups(const std::vector<float>& dense, int nm, int F, int kReadEnd,
+                                std::vector<int>& meta, std::vector<float>& melw) {
+    const int ng = (nm + 31) / 32;
+    meta.assign(2 * kMaxMelGroups + 32 * ng, 0);
+    melw.clear();
+    std::vector<int> lo(nm, 0), len(nm, 0);
+    for (int m = 0; m < nm; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < F; ++k)
+            if (dense[(size_t)m * F + k] != 0.0f) { if (first < 0) first = k; last = k; }
+        if (first >= 0) { lo[m] = first; len[m] = last - first + 1; }
+    }
+    auto qof = [](int k) { return k + (k >> 4); };
+    for (int g = 0; g < ng; ++g) {
+        int ql[32], qlen[32];
+        int gmax = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int m = 32 * g + l;
+            if (m < nm && len[m] > 0) {
+                ql[l] = qof(lo[m]);
+                qlen[l] = qof(lo[m] + len[m] - 1) - ql[l] + 1;
+            } else { ql[l] = 0; qlen[l] = 0; }
+            if (qlen[l] > gmax) gmax = qlen[l];
+        }
+        // Shift each lane's first tap down (zero weights in front) so that the 32 lanes
+        // start on 32 different banks: the gather is then conflict-free at every step.
+        // Bipartite matching lanes -> banks; grow the common length G until one exists.
+        int G = (gmax + 3) & ~3, shiftv[32];
+        for (int l = 0; l < 32; ++l) shiftv[l] = 0;
+        bool ok = (G == 0);
+        for (int tries = 0; !ok && tries < 12; ++tries, G += 4) {
+            std::vector<std::vector<int>> opt(32);   // candidate shifts per lane
+            bool feasible = true;
+            for (int l = 0; l < 32; ++l) {
+                if (qlen[l] == 0) { for (int s = 0; s < 32; ++s) opt[l].push_back(-s); continue; }  // start = s
+                const int smin = std::max(0, ql[l] + G - kReadEnd);
+                const int smax = std::min(G - qlen[l], ql[l]);
+                if (smin > smax) { feasible = false; break; }
+                for (int s = smin; s <= smax && s < smin + 32; ++s) opt[l].push_back(s);
+            }
+            if (!feasible) continue;
+            int owner[32]; for (int& o : owner) o = -1;
+            auto bank_of = [&](int l, int s) { return ((qlen[l] == 0 ? -s : ql[l] - s) % 32 + 32) % 32; };
+            std::vector<char> seen(32);
+            std::function<bool(int)> aug = [&](int l) -> bool {
+                for (int s : opt[l]) {
+                    const int bk = bank_of(l, s);
+                    if (seen[bk]) continue;
+                    seen[bk] = 1;
+                    if (owner[bk] < 0 || aug(owner[bk])) { owner[bk] = l; return true; }
+                }
+                return false;
+            };
+            int matched = 0;
+            for (int l = 0; l < 32; ++l) { std::fill(seen.begin(), seen.end(), 0); if (aug(l)) ++matched; }
+            if (matched == 32) {
+                for (int bk = 0; bk < 32; ++bk) {
+                    const int l = owner[bk];
+                    for (int s : opt[l]) if (bank_of(l, s) == bk) { shiftv[l] = s; break; }
+                }
+                ok = true;
+                break;
+            }
+        }
+        if (!ok) {   // no conflict-free placement: keep the natural starts (still correct)
+            G = (gmax + 3) & ~3;
+            for (int l = 0; l < 32; ++l) shiftv[l] = std::max(0, ql[l] + G - kReadEnd);
+        }
+        meta[g] = G / 4;
+        meta[kMaxMelGroups + g] = (int)melw.size();
+        const size_t base = melw.size();
+        melw.resize(base + (size_t)32 * G, 0.0f);
+        for (int l = 0; l < 32; ++l) {
+            const int m = 32 * g + l;
+            const int start = (qlen[l] == 0) ? -shiftv[l] : ql[l] - shiftv[l];
+            meta[2 * kMaxMelGroups + 32 * g + l] = start;
+            if (qlen[l] == 0) continue;
+            for (int q = ql[l]; q < ql[l] + qlen[l]; ++q) {
+                if (q % 17 == 16) continue;                     // pad slot
+                const int k = q - q / 17, i = q - start;
+                melw[base + ((size_t)(i / 4) * 32 + l) * 4 + (i % 4)] = dense[(size_t)m * F + k];
+            }
+        }
+    }
 }
 
 template <class T>
@@ -238,7 +330,7 @@ void hlmc_plan_destroy(hlmc_plan* plan) {
         cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr); cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    cudaFree(plan->d_fast); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
+    cudaFree(plan->d_fast); cudaFree(plan->d_fast4); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
     cudaFree(plan->d_mel_lo); cudaFree(plan->d_mel_len); cudaFree(plan->d_mel_off); cudaFree(plan->d_mel_w);
     cudaFree(plan->d_dct_t); cudaFree(plan->d_chroma_fb); cudaFree(plan->d_edges);
     delete plan;
@@ -336,81 +428,10 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         ft.n_groups = ng;
         // meta: [0..7] float4 steps per group, [8..15] weight offset per group, then the
         // (shifted) first tap of every (group, lane) in the padded layout q(k) = k + k/16
-        std::vector<int> meta(2 * kMaxMelGroups + 32 * ng, 0);
+        std::vector<int> meta;
         std::vector<float> melw;
-        auto qof = [](int k) { return k + (k >> 4); };
         const int kReadEnd = 1105;           // the kernel keeps scratch [0, 1105) finite
-        for (int g = 0; g < ng; ++g) {
-            int ql[32], qlen[32];
-            int gmax = 0;
-            for (int l = 0; l < 32; ++l) {
-                const int m = 32 * g + l;
-                if (m < nm && len[m] > 0) {
-                    ql[l] = qof(lo[m]);
-                    qlen[l] = qof(lo[m] + len[m] - 1) - ql[l] + 1;
-                } else { ql[l] = 0; qlen[l] = 0; }
-                if (qlen[l] > gmax) gmax = qlen[l];
-            }
-            // Shift each lane's first tap down (zero weights in front) so that the 32 lanes
-            // start on 32 different banks: the gather is then conflict-free at every step.
-            // Bipartite matching lanes -> banks; grow the common length G until one exists.
-            int G = (gmax + 3) & ~3, shiftv[32];
-            for (int l = 0; l < 32; ++l) shiftv[l] = 0;
-            bool ok = (G == 0);
-            for (int tries = 0; !ok && tries < 12; ++tries, G += 4) {
-                std::vector<std::vector<int>> opt(32);   // candidate shifts per lane
-                bool feasible = true;
-                for (int l = 0; l < 32; ++l) {
-                    if (qlen[l] == 0) { for (int s = 0; s < 32; ++s) opt[l].push_back(-s); continue; }  // start = s
-                    const int smin = std::max(0, ql[l] + G - kReadEnd);
-                    const int smax = std::min(G - qlen[l], ql[l]);
-                    if (smin > smax) { feasible = false; break; }
-                    for (int s = smin; s <= smax && s < smin + 32; ++s) opt[l].push_back(s);
-                }
-                if (!feasible) continue;
-                int owner[32]; for (int& o : owner) o = -1;
-                auto bank_of = [&](int l, int s) { return ((qlen[l] == 0 ? -s : ql[l] - s) % 32 + 32) % 32; };
-                std::vector<char> seen(32);
-                std::function<bool(int)> aug = [&](int l) -> bool {
-                    for (int s : opt[l]) {
-                        const int bk = bank_of(l, s);
-                        if (seen[bk]) continue;
-                        seen[bk] = 1;
-                        if (owner[bk] < 0 || aug(owner[bk])) { owner[bk] = l; return true; }
-                    }
-                    return false;
-                };
-                int matched = 0;
-                for (int l = 0; l < 32; ++l) { std::fill(seen.begin(), seen.end(), 0); if (aug(l)) ++matched; }
-                if (matched == 32) {
-                    for (int bk = 0; bk < 32; ++bk) {
-                        const int l = owner[bk];
-                        for (int s : opt[l]) if (bank_of(l, s) == bk) { shiftv[l] = s; break; }
-                    }
-                    ok = true;
-                    break;
-                }
-            }
-            if (!ok) {   // no conflict-free placement: keep the natural starts (still correct)
-                G = (gmax + 3) & ~3;
-                for (int l = 0; l < 32; ++l) shiftv[l] = std::max(0, ql[l] + G - kReadEnd);
-            }
-            meta[g] = G / 4;
-            meta[kMaxMelGroups + g] = (int)melw.size();
-            const size_t base = melw.size();
-            melw.resize(base + (size_t)32 * G, 0.0f);
-            for (int l = 0; l < 32; ++l) {
-                const int m = 32 * g + l;
-                const int start = (qlen[l] == 0) ? -shiftv[l] : ql[l] - shiftv[l];
-                meta[2 * kMaxMelGroups + 32 * g + l] = start;
-                if (qlen[l] == 0) continue;
-                for (int q = ql[l]; q < ql[l] + qlen[l]; ++q) {
-                    if (q % 17 == 16) continue;                     // pad slot
-                    const int k = q - q / 17, i = q - start;
-                    melw[base + ((size_t)(i / 4) * 32 + l) * 4 + (i % 4)] = pl->mel_dense[(size_t)m * F + k];
-                }
-            }
-        }
+        build_banded_groups(pl->mel_dense, nm, F, kReadEnd, meta, melw);
         auto r4 = [](int x) { return (x + 3) & ~3; };
         ft.tw1 = 0;
         ft.tw2 = ft.tw1 + 31 * 32 * 2;
@@ -448,6 +469,69 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         pl->ft = ft;
         UP(d_fast, blob)
         pl->fast_ok = fast_smem_bytes(ft, 8, N, p.hop_length, nm) <= 227 * 1024;
+    }
+    // register-FFT tables for n_fft = 4096 (frames_fast_4096): full-length periodic Hann, n_mels <= 128
+    if (N == 4096) {
+        bool hann = (p.win_length == N);
+        for (int i = 0; window && hann && i < N; ++i)
+            if (fabs(window[i] - (0.5 - 0.5 * cos(2.0 * M_PI * double(i) / double(N)))) > 1e-9) hann = false;
+        if (hann && nm <= 128) {
+            Fast4Tables ft{};
+            ft.n_groups = (nm + 31) / 32;
+            // filterbank columns de-interleaved: even bins 2k' (k' = 0..1024), odd bins 2k'+1 (k' = 0..1023)
+            const int Fh = 1025, kReadEnd = 1105;
+            std::vector<float> dense[2] = {std::vector<float>((size_t)nm * Fh, 0.0f), std::vector<float>((size_t)nm * Fh, 0.0f)};
+            for (int m = 0; m < nm; ++m)
+                for (int k = 0; k < F; ++k) dense[k & 1][(size_t)m * Fh + (k >> 1)] = pl->mel_dense[(size_t)m * F + k];
+            std::vector<int> meta[2];
+            std::vector<float> melw[2];
+            for (int par = 0; par < 2; ++par) build_banded_groups(dense[par], nm, Fh, kReadEnd, meta[par], melw[par]);
+            auto r4 = [](int x) { return (x + 3) & ~3; };
+            ft.tw1 = 0;
+            ft.tw0 = ft.tw1 + 31 * 32 * 2;
+            ft.base = ft.tw0 + 1024 * 2;
+            ft.hann_cs = ft.base + 2 * 32 * 2;
+            int at = ft.hann_cs + 32 * 4;
+            for (int par = 0; par < 2; ++par) {
+                ft.mel_meta[par] = at;
+                ft.mel_w[par] = r4(at + (int)meta[par].size());
+                at = r4(ft.mel_w[par] + (int)melw[par].size());
+            }
+            ft.total = at;
+            std::vector<float> blob(ft.total, 0.0f);
+            for (int k1 = 1; k1 < 32; ++k1)
+                for (int l = 0; l < 32; ++l) {
+                    const double th = 2.0 * M_PI * double((l * k1) % 1024) / 1024.0;
+                    blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 0] = float(cos(th));
+                    blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 1] = float(-sin(th));
+                }
+            for (int m = 0; m < 1024; ++m) {
+                const double th = 2.0 * M_PI * double(m) / 2048.0;               // W_2048^m
+                blob[ft.tw0 + 2 * m + 0] = float(cos(th));
+                blob[ft.tw0 + 2 * m + 1] = float(-sin(th));
+            }
+            for (int l = 0; l < 32; ++l) {
+                const double t0 = 2.0 * M_PI * double(16 * l) / 2048.0;          // -i * W_2048^(16 l)
+                const double t1 = 2.0 * M_PI * double(32 * l + 1) / 4096.0;      // -i * W_4096^(32 l + 1)
+                blob[ft.base + 2 * l + 0] = float(-sin(t0));
+                blob[ft.base + 2 * l + 1] = float(-cos(t0));
+                blob[ft.base + 2 * (32 + l) + 0] = float(-sin(t1));
+                blob[ft.base + 2 * (32 + l) + 1] = float(-cos(t1));
+                const double te = 2.0 * M_PI * double(2 * l) / double(N), to = 2.0 * M_PI * double(2 * l + 1) / double(N);
+                blob[ft.hann_cs + 4 * l + 0] = float(cos(te));
+                blob[ft.hann_cs + 4 * l + 1] = float(cos(to));
+                blob[ft.hann_cs + 4 * l + 2] = float(sin(te));
+                blob[ft.hann_cs + 4 * l + 3] = float(sin(to));
+            }
+            for (int par = 0; par < 2; ++par) {
+                memcpy(&blob[ft.mel_meta[par]], meta[par].data(), meta[par].size() * 4);
+                if (!melw[par].empty()) memcpy(&blob[ft.mel_w[par]], melw[par].data(), melw[par].size() * 4);
+            }
+            pl->ft4 = ft;
+            UP(d_fast4, blob)
+            pl->fast4_ok = fast4_smem_bytes(ft) <= 227 * 1024;
+            pl->fast_ok = pl->fast4_ok;
+        }
     }
     // register-FFT tables for n_fft = 1024 / 512: L = n_fft / 64 lanes per frame (frames_sub kernel)
     if (N == 1024 || N == 512) {
@@ -603,6 +687,10 @@ static int run_frames(hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, 
     if (d_status) CK(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
     if (pl->fast_ok && !pl->force_generic && d_spec == nullptr) {
         if (pl->p.n_fft == kFastNfft) CK(launch_frames_fast(a, pl->d_fast, pl->ft, pl->num_sms, st));
+        else if (pl->p.n_fft == 4096) {
+            if (cand) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs n_fft = 2048");
+            CK(launch_frames_fast4096(a, pl->d_fast4, pl->ft4, pl->num_sms, st));
+        }
         else CK(launch_frames_sub(a, pl->d_fast, pl->ft, pl->num_sms, st));
     } else {
         if (cand) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs the register-FFT kernel");

@@ -26,6 +26,18 @@ struct FastTables {
     int nowin;      // floats before the window (multiple of 4)
 };
 
+// Tables of the n_fft = 4096 register-FFT kernel (frames_fast_4096).
+struct Fast4Tables {
+    int tw1;          // 31*32 float2: W_1024^(lane*k1)
+    int tw0;          // 1024 float2: W_2048^m, the radix-2 twiddle of the odd-bin pass
+    int base;         // 2*32 float2: -i W_2048^(16 lane) (even bins), -i W_4096^(32 lane + 1) (odd bins)
+    int hann_cs;      // 32 float4: (cos, cos', sin, sin') of 2*pi*(2*lane + {0,1}) / 4096
+    int mel_meta[2];  // per parity: int32 gmax[8], goff[8], qlo[32*n_groups]
+    int mel_w[2];     // per parity: banded weights of the de-interleaved filterbank columns
+    int total;        // floats, multiple of 4
+    int n_groups;     // <= 4 (n_mels <= 128)
+};
+
 struct FrameArgs {
     const float* wave;      // (B, pitch)
     long long pitch;
@@ -84,6 +96,9 @@ struct DbArgs {
 // launchers (all asynchronous on `stream`; return cudaError_t)
 cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                int num_sms, cudaStream_t stream);
+cudaError_t launch_frames_fast4096(const FrameArgs& a, const float* d_tables, const Fast4Tables& ft, int num_sms,
+                                   cudaStream_t stream);
+int fast4_smem_bytes(const Fast4Tables& ft);
 cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
                               cudaStream_t stream);
 int sub_smem_bytes(const FastTables& ft, int nwarps, int L);

@@ -200,15 +200,15 @@ struct WarpState {
 // aligned (16-byte aligned source, 0..3 leading floats).  Returns the shift, or -1 if the frame has to be
 // built by hand.
 __device__ __forceinline__ int issue_frame_tma(const FrameArgs& a, const WarpState& w, float* land,
-                                               const float* clip, int t) {
+                                               const float* clip, int t, int nfft = kFastNfft) {
     const int fs = t * a.hop - a.pad;
-    const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
+    const bool interior = (fs >= 0) && (fs + nfft <= a.n);
     const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
     const int shift = (int)((addr & 15) >> 2);
     if (!interior || (shift & 1)) return -1;
     if (w.lane == 0) {
         const float* src0 = reinterpret_cast<const float*>(addr & ~uintptr_t(15));
-        const int tot = shift + kFastNfft;
+        const int tot = shift + nfft;
         const int bulk = tot & ~3;
         for (int i = bulk; i < tot; ++i) land[i] = __ldg(src0 + i);     // <= 3 tail floats
         fence_proxy_async_smem();       // order earlier generic accesses before the async write
@@ -667,6 +667,412 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
         return pip ? launch_fast_nw<8, true, false>(a, d_tables, ft, num_sms, stream)
                    : launch_fast_nw<8, false, false>(a, d_tables, ft, num_sms, stream);
     return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------
+// Register-FFT path for n_fft = 4096 (full-length periodic Hann window).  One warp per frame as in
+// frames_fast_2048, but the 2048-point complex FFT of z[m] = x[2m] + i x[2m+1] does not fit the
+// registers of one warp, so it is split by one radix-2 decimation-in-frequency step into two
+// 1024-point transforms that run one after the other through the same 32 x 32 machinery:
+//     pass 0:  a[m] = z[m] + z[m+1024]                      -> Z[2k']   (even bins of the real FFT)
+//     pass 1:  b[m] = (z[m] - z[m+1024]) * W_2048^m         -> Z[2k'+1] (odd bins)
+// b is parked in the slot of z[m] (only this lane ever reads it), the Hann window of the second half
+// is 0.5 - w of the first (no second synthesis), each pass does its own real-FFT split (the partner of
+// bin k is 2048 - k, which has the same parity), its own share of the moments and its own half of the
+// mel gather (filterbank columns de-interleaved on the host), so only the 32 magnitudes per lane that
+// rolloff needs in bin order are carried from pass 0 to pass 1 (through shared memory).
+// Shared memory per warp: 4100 floats landing zone (first half becomes b), 2180 floats transpose /
+// power-spectrum scratch (overlapping the second half of the landing zone), 1056 floats magnitudes.
+// ---------------------------------------------------------------------------
+constexpr int k4Nfft = 4096;
+constexpr int k4T = 2052;                        // transposes / power scratch start (past b, 16-byte aligned)
+constexpr int k4Sev = k4T + 2180;                // pass-0 magnitudes, [lane][33]
+constexpr int k4WarpFloats = k4Sev + 32 * 33;    // 5288
+constexpr int k4Warps = 8;
+
+int fast4_smem_bytes(const Fast4Tables& ft) { return (((2 * k4Warps + 3) & ~3) + ft.total + k4Warps * k4WarpFloats) * 4; }
+
+// phases 1-5 of one 1024-point pass: v[j] = element lane + 32 j on entry; on exit v[i] / v[16+i] hold the
+// lane's low run k' = 16 lane + i and its partners (pass 0: 1024 - k', pass 1: 1023 - k').
+template <int PASS>
+__device__ __forceinline__ void fft1024_regroup(float2 (&v)[32], float2* __restrict__ sc2,
+                                                const float2* __restrict__ s_tw1, int lane, float2& e512) {
+    fftreg2::fft_dif<32>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) {
+        const float2 tw = s_tw1[(k1 - 1) * 32 + lane];
+        const int p = pos32(k1);
+        v[p] = fftreg2::cmul(v[p], tw.x, tw.y);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) sc2[lane * 33 + k1] = v[pos32(k1)];
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) v[n2] = sc2[n2 * 33 + lane];
+    __syncwarp();
+    fftreg2::fft_dif<32>(v);
+    const int zw_base = lane + (lane >> 4);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) sc2[zw_base + 34 * k2] = v[pos32(k2)];
+    __syncwarp();
+    const int zlo_base = 17 * lane;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = sc2[zlo_base + i];
+    if (PASS == 0) {
+        const int zhi_base = 17 * (63 - lane) + 16, zhi0 = (lane == 0) ? 0 : 17 * (64 - lane);
+        v[16] = sc2[zhi0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) v[16 + i] = sc2[zhi_base - i];
+        e512 = sc2[544];
+    } else {
+        const int zhi_base = 17 * (63 - lane) + 15;          // k' = 1023 - 16 lane - i
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[16 + i] = sc2[zhi_base - i];
+    }
+    __syncwarp();
+}
+
+// real-FFT split of one pass: P[i] = (|X[k]|^2, |X[partner]|^2), S[i] the magnitudes; moments of the
+// magnitudes about the run centres in units of k' (the caller rescales to bins).
+__device__ __forceinline__ void split_pass(const float2 (&v)[32], float2 tw_base, float2 (&P)[16], float2 (&S)[16],
+                                           float2& M0, float2& M1, float2& M2) {
+    M0 = make_float2(0.f, 0.f); M1 = M0; M2 = M0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float2 tw = (i == 0) ? tw_base
+                                   : fftreg2::cmul_conj(tw_base, float(fftreg::cos2pi(i, 2048)), float(fftreg::sin2pi(i, 2048)));
+        const float2 za_ = v[i], zb_ = v[16 + i];
+        const float2 e = __fadd2_rn(za_, make_float2(zb_.x, -zb_.y));
+        const float2 d = __fadd2_rn(za_, make_float2(-zb_.x, zb_.y));
+        const float2 tt = fftreg2::cmul(d, tw.x, tw.y);
+        const float2 xa = __fadd2_rn(e, tt), xb = __fadd2_rn(e, make_float2(-tt.x, -tt.y));
+        const float2 pw = make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
+        const float2 sq = make_float2(fast_sqrt(pw.x), fast_sqrt(pw.y));
+        P[i] = pw;
+        S[i] = sq;
+        const float dd = float(i) - 7.5f;
+        M0 = __fadd2_rn(M0, sq);
+        M1 = __ffma2_rn(make_float2(sq.x, -sq.y), make_float2(dd, dd), M1);
+        M2 = __ffma2_rn(sq, make_float2(dd * dd, dd * dd), M2);
+    }
+}
+
+__global__ void __launch_bounds__(k4Warps * 32, 1)
+frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fast4Tables ft) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NW = k4Warps, NT = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
+    float* tab = smem + ((2 * NW + 3) & ~3);
+    const float2* s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
+    const float2* s_tw0 = reinterpret_cast<const float2*>(tab + ft.tw0);
+    const float2* s_base = reinterpret_cast<const float2*>(tab + ft.base);
+    const float4* s_hcs = reinterpret_cast<const float4*>(tab + ft.hann_cs);
+    float* sc = tab + ft.total + warp * k4WarpFloats;       // landing zone; b after pass 0's first phase
+    float* scT = sc + k4T;                                  // transposes, then the pass's power spectrum
+    float2* scT2 = reinterpret_cast<float2*>(scT);
+    float* sev = sc + k4Sev;
+
+    for (int i = tid; i < ft.total / 4; i += NT)
+        reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
+    for (int i = tid; i < NW * k4WarpFloats; i += NT) (tab + ft.total)[i] = 0.0f;
+    if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncthreads();
+
+    const long long total = (long long)a.B * a.T;
+    const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
+    const long long c0 = (long long)blockIdx.x * per_cta;
+    const long long g1 = (c0 + per_cta < total) ? c0 + per_cta : total;
+    const long long g0 = c0 + warp;
+    if (g0 >= g1) return;
+    int b = (int)(g0 / a.T);
+    int t = (int)(g0 - (long long)b * a.T);
+    float clip_max = 0.0f;
+    WarpState w{};
+    w.sc = sc; w.sc2 = reinterpret_cast<float2*>(sc); w.mbar = mbar; w.parity = 0; w.lane = lane;
+    const float zthr = a.zcr_thr;
+    const float4 hcs = s_hcs[lane];
+    const float2 hc = make_float2(hcs.x, hcs.y), hs = make_float2(hcs.z, hcs.w);
+
+    for (long long g = g0; g < g1; g += NW) {
+        const float* clip = a.wave + (long long)b * a.pitch;
+        const int fs = t * a.hop - a.pad;
+        // ---- stage the 4096 samples
+        int zc_edge = -1;
+        int off = issue_frame_tma(a, w, sc, clip, t, k4Nfft);
+        if (off >= 0) {
+            mbar_wait(mbar, w.parity);
+            w.parity ^= 1u;
+        } else {
+            int zc = 0;
+            unsigned prev_last = 0u;
+            for (int c0s = 0; c0s < k4Nfft / 32; c0s += 8) {
+                float ve[8], vp[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ve[u] = sample_edge(clip, a.n, fs + 32 * (c0s + u) + lane);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int s = fs + 32 * (c0s + u) + lane;
+                    const bool inside = (s >= 0) && (s < a.n);
+                    vp[u] = inside ? ve[u] : ((a.pad_mode == 0) ? 0.0f : (a.pad_mode == 1) ? __ldg(clip + reflect_index(s, a.n)) : ve[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    sc[32 * (c0s + u) + lane] = vp[u];
+                    const unsigned msk = __ballot_sync(FULL, ve[u] < -zthr);
+                    zc += __popc((msk ^ (msk >> 1)) & 0x7fffffffu);
+                    if (c0s + u > 0) zc += ((msk & 1u) != prev_last) ? 1 : 0;
+                    prev_last = msk >> 31;
+                }
+            }
+            zc_edge = zc;
+            off = 0;
+            __syncwarp();
+        }
+
+        float2 v[32];
+        float2 P[16], S[16];
+        float2 A0, A1, A2, B0, B1, B2;          // moments of the even (A) and odd (B) bins, (low run, high run)
+        float ss;
+        int zc;
+        float macc[kMaxMelGroups > 4 ? 4 : kMaxMelGroups];
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) macc[gi] = 0.0f;
+
+        // ================= pass 0: even bins =================
+        {
+            float2* L2 = reinterpret_cast<float2*>(sc + off);
+            const float2 zt = make_float2(zthr, zthr), quarter = make_float2(0.25f, 0.25f), half = make_float2(0.5f, 0.5f);
+            float2 ss2 = make_float2(0.f, 0.f);
+            unsigned za0 = 0u, zb0 = 0u, za1 = 0u, zb1 = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float2 x0 = L2[lane + 32 * j], x1 = L2[lane + 32 * j + 1024];
+                // 0.5 * hann of samples 2(lane + 32 j) + c:  0.25 - 0.25 cos(theta + 2 pi j / 64); second half = 0.5 - that
+                const float cj = -0.25f * float(fftreg::cos2pi(j, 64)), sj = 0.25f * float(fftreg::sin2pi(j, 64));
+                float2 w0;
+                if (j == 0) w0 = __ffma2_rn(hc, make_float2(cj, cj), quarter);
+                else if (j == 16) w0 = __ffma2_rn(hs, make_float2(sj, sj), quarter);
+                else w0 = __ffma2_rn(hc, make_float2(cj, cj), __ffma2_rn(hs, make_float2(sj, sj), quarter));
+                const float2 w1 = __fadd2_rn(half, make_float2(-w0.x, -w0.y));
+                ss2 = __ffma2_rn(x0, x0, ss2);
+                ss2 = __ffma2_rn(x1, x1, ss2);
+                const float2 t0 = __fadd2_rn(x0, zt), t1 = __fadd2_rn(x1, zt);
+                za0 = __funnelshift_l(__float_as_uint(t0.x), za0, 1);
+                zb0 = __funnelshift_l(__float_as_uint(t0.y), zb0, 1);
+                za1 = __funnelshift_l(__float_as_uint(t1.x), za1, 1);
+                zb1 = __funnelshift_l(__float_as_uint(t1.y), zb1, 1);
+                const float2 z0 = __fmul2_rn(x0, w0), z1 = __fmul2_rn(x1, w1);
+                v[j] = __fadd2_rn(z0, z1);
+                L2[lane + 32 * j] = __fadd2_rn(z0, make_float2(-z1.x, -z1.y));     // b (before its twiddle)
+            }
+            ss = warp_sum(ss2.x + ss2.y);
+            {
+                // rows 0..31 (first half) in word 0, rows 32..63 in word 1, row r at bit 31 - (r & 31)
+                unsigned zn0 = __shfl_sync(FULL, za0, (lane + 1) & 31);
+                unsigned zn1 = __shfl_sync(FULL, za1, (lane + 1) & 31);
+                unsigned m1 = FULL;
+                if (lane == 31) { zn0 = (zn0 << 1) | (zn1 >> 31); zn1 <<= 1; m1 = 0xfffffffeu; }
+                zc = __popc(za0 ^ zb0) + __popc(za1 ^ zb1) + __popc(zb0 ^ zn0) + __popc((zb1 ^ zn1) & m1);
+                zc = warp_sum_i(zc);
+                if (zc_edge >= 0) zc = zc_edge;
+            }
+            __syncwarp();
+        }
+        float2 e512;
+        fft1024_regroup<0>(v, scT2, s_tw1, lane, e512);
+        split_pass(v, s_base[lane], P, S, A0, A1, A2);
+        // bin 1024 (k' = 512) pairs with itself
+        const float p1024 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
+        const float s1024 = fast_sqrt(p1024);
+        // magnitudes of the even bins for rolloff's in-order search, power of the even bins for the mel gather
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { sev[lane * 33 + i] = S[i].x; sev[lane * 33 + 16 + i] = S[i].y; }
+        {
+            const bool mag = a.use_mag != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) scT[17 * lane + i] = mag ? S[i].x : P[i].x;
+            scT[17 * (64 - lane)] = mag ? S[0].y : P[0].y;
+#pragma unroll
+            for (int i = 1; i < 16; ++i) scT[17 * (63 - lane) + 16 - i] = mag ? S[i].y : P[i].y;
+            if (lane == 31) scT[544] = mag ? s1024 : p1024;
+            scT[17 * lane + 16] = 0.0f;
+            scT[17 * (63 - lane) + 16] = 0.0f;
+            if (lane < 16) scT[1089 + lane] = 0.0f;
+            __syncwarp();
+        }
+        if (a.mel_out != nullptr) {
+            const int* meta = reinterpret_cast<const int*>(tab + ft.mel_meta[0]);
+            const float* melw = tab + ft.mel_w[0];
+            for (int gi = 0; gi < ft.n_groups; ++gi) {
+                const int n4 = meta[gi];
+                const float4* wp = reinterpret_cast<const float4*>(melw + meta[kMaxMelGroups + gi]) + lane;
+                const float* pp = scT + meta[2 * kMaxMelGroups + 32 * gi + lane];
+                float2 a01 = make_float2(0.f, 0.f), a23 = a01;
+                mel_steps(n4, wp, pp, a01, a23);
+                a01 = __fadd2_rn(a01, a23);
+                macc[gi & 3] = (gi < 4) ? a01.x + a01.y : macc[gi & 3];
+            }
+        }
+        __syncwarp();                       // the power scratch is read: the transposes of pass 1 may overwrite it
+
+        // ================= pass 1: odd bins =================
+        {
+            const float2* L2 = reinterpret_cast<const float2*>(sc + off);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float2 bq = L2[lane + 32 * j];
+                const float2 tw = s_tw0[lane + 32 * j];          // W_2048^m = (cos, -sin)
+                v[j] = fftreg2::cmul(bq, tw.x, tw.y);
+            }
+            __syncwarp();
+        }
+        fft1024_regroup<1>(v, scT2, s_tw1, lane, e512);
+        float2 So[16];
+        split_pass(v, s_base[32 + lane], P, So, B0, B1, B2);
+        {
+            const bool mag = a.use_mag != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) scT[17 * lane + i] = mag ? So[i].x : P[i].x;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) scT[17 * (63 - lane) + 15 - i] = mag ? So[i].y : P[i].y;
+            scT[17 * lane + 16] = 0.0f;
+            scT[17 * (63 - lane) + 16] = 0.0f;
+            if (lane < 16) scT[1088 + lane] = 0.0f;
+            __syncwarp();
+        }
+        if (a.mel_out != nullptr) {
+            const int* meta = reinterpret_cast<const int*>(tab + ft.mel_meta[1]);
+            const float* melw = tab + ft.mel_w[1];
+            float wmax = 0.0f;
+            const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
+            float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
+                                            : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+            for (int gi = 0; gi < ft.n_groups; ++gi) {
+                const int n4 = meta[gi];
+                const float4* wp = reinterpret_cast<const float4*>(melw + meta[kMaxMelGroups + gi]) + lane;
+                const float* pp = scT + meta[2 * kMaxMelGroups + 32 * gi + lane];
+                float2 a01 = make_float2(0.f, 0.f), a23 = a01;
+                mel_steps(n4, wp, pp, a01, a23);
+                a01 = __fadd2_rn(a01, a23);
+                const float acc = (a01.x + a01.y) + macc[gi & 3];
+                const int m = 32 * gi + lane;
+                if (m < a.n_mels) outb[(size_t)m * mstride] = acc;
+                wmax = fmaxf(wmax, acc);
+            }
+            clip_max = fmaxf(clip_max, wmax);
+        }
+
+        // ---- centroid / bandwidth: even bins k = 32 lane + 15 + 2 d (low), 2048 - 32 lane - 15 - 2 d (high);
+        //      odd bins k = 32 lane + 16 + 2 d (low), 2047 - 32 lane - 15 - 2 d (high); d = i - 7.5
+        const float kel = 32.0f * lane + 15.0f, keh = 2033.0f - 32.0f * lane;
+        const float kol = 32.0f * lane + 16.0f, koh = 2032.0f - 32.0f * lane;
+        float s0 = (A0.x + A0.y) + (B0.x + B0.y);
+        float s1 = fmaf(kel, A0.x, 2.0f * A1.x) + fmaf(keh, A0.y, 2.0f * A1.y) +
+                   fmaf(kol, B0.x, 2.0f * B1.x) + fmaf(koh, B0.y, 2.0f * B1.y);
+        if (lane == 31) { s0 += s1024; s1 = fmaf(1024.0f, s1024, s1); }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;
+        const float cen = s1 / denom;
+        float q;
+        {
+            // sum s (2 d + (kc - c))^2 = 4 m2 + 4 (kc - c) m1 + (kc - c)^2 m0
+            const float d0 = kel - cen, d1 = keh - cen, d2 = kol - cen, d3 = koh - cen;
+            q = fmaf(d0, fmaf(d0, A0.x, 4.0f * A1.x), 4.0f * A2.x) + fmaf(d1, fmaf(d1, A0.y, 4.0f * A1.y), 4.0f * A2.y) +
+                fmaf(d2, fmaf(d2, B0.x, 4.0f * B1.x), 4.0f * B2.x) + fmaf(d3, fmaf(d3, B0.y, 4.0f * B1.y), 4.0f * B2.y);
+            if (lane == 31) { const float dm = 1024.0f - cen; q = fmaf(dm * dm, s1024, q); }
+            q = warp_sum(q);
+        }
+        const float bw = sqrtf(fmaxf(q, 0.0f) / denom);
+
+        // ---- rolloff: lane totals over [32 lane, 32 lane + 32) and (2016 - 32 lane, 2048 - 32 lane]
+        int rbin;
+        {
+            const float tl = A0.x + B0.x, th = A0.y + B0.y;
+            float pl = tl;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float tv = __shfl_up_sync(FULL, pl, d);
+                if (lane >= d) pl += tv;
+            }
+            float ph = th;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float tv = __shfl_down_sync(FULL, ph, d);
+                if (lane + d < 32) ph += tv;
+            }
+            const float tot_lo = __shfl_sync(FULL, pl, 31);
+            const float tot_hi = __shfl_sync(FULL, ph, 0);
+            const float mid = tot_lo + s1024;
+            const float thr = a.roll_percent * (mid + tot_hi);
+            const unsigned lo_mask = __ballot_sync(FULL, pl >= thr);
+            if (lo_mask) {
+                const int tlane = __ffs(lo_mask) - 1;
+                float cum = pl - tl;
+                int cnt = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {      // ascending: even 32 lane + 2 i, odd 32 lane + 2 i + 1
+                    cum += sev[lane * 33 + i]; cnt += (cum < thr) ? 1 : 0;
+                    cum += So[i].x; cnt += (cum < thr) ? 1 : 0;
+                }
+                rbin = __shfl_sync(FULL, 32 * lane + min(cnt, 31), tlane);
+            } else if (mid >= thr) {
+                rbin = 1024;
+            } else {
+                const unsigned hi_mask = __ballot_sync(FULL, mid + ph >= thr);
+                if (hi_mask) {
+                    const int tlane = 31 - __clz(hi_mask);
+                    float cum = mid + (ph - th);
+                    int cnt = 0;
+#pragma unroll
+                    for (int i = 15; i >= 0; --i) {  // ascending: odd 2047 - 32 lane - 2 i, even 2048 - 32 lane - 2 i
+                        cum += So[i].y; cnt += (cum < thr) ? 1 : 0;
+                        cum += sev[lane * 33 + 16 + i]; cnt += (cum < thr) ? 1 : 0;
+                    }
+                    // the run's ascending bins start at 2017 - 32 lane
+                    rbin = __shfl_sync(FULL, 2017 - 32 * lane + min(cnt, 31), tlane);
+                } else {
+                    rbin = 2048;
+                }
+            }
+        }
+
+        if (lane == 0) {
+            if (a.stats != nullptr) {
+                float* st = a.stats + (size_t)b * 5 * a.T + t;
+                st[0] = cen * a.binhz;
+                st[(size_t)a.T] = bw * a.binhz;
+                st[(size_t)2 * a.T] = float(rbin) * a.binhz;
+                st[(size_t)3 * a.T] = float(zc) * (1.0f / float(k4Nfft));
+                st[(size_t)4 * a.T] = sqrtf(ss * (1.0f / float(k4Nfft)));
+            }
+            if (a.status != nullptr && !(fabsf(ss) <= 3.0e38f)) atomicOr(a.status + b, 1);
+        }
+        const bool last = (t + NW >= a.T) || (g + NW >= g1);
+        if (last && a.clipmax != nullptr && a.mel_out != nullptr) {
+            const float m = warp_max(clip_max);
+            if (lane == 0) atomicMax(reinterpret_cast<int*>(a.clipmax) + b, __float_as_int(m));
+            clip_max = 0.0f;
+        }
+        t += NW;
+        while (t >= a.T) { t -= a.T; ++b; }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_frames_fast4096(const FrameArgs& a, const float* d_tables, const Fast4Tables& ft, int num_sms,
+                                   cudaStream_t stream) {
+    const int smem = fast4_smem_bytes(ft);
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const long long frames = (long long)a.B * a.T;
+    if (frames <= 0) return cudaSuccess;
+    long long grid = (frames + k4Warps - 1) / k4Warps;
+    if (grid > num_sms) grid = num_sms;
+    frames_fast_4096<<<(unsigned)grid, k4Warps * 32, smem, stream>>>(a, d_tables, ft);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------

@@ -458,10 +458,11 @@ def test_device_standard_scaler_matches_sklearn(built, tmp_path):
     assert a.shape == (6, 128, 1024) and a.dtype == np.float32 and np.abs(a - b).max() <= 5e-6
 
 
-@pytest.mark.parametrize("n_fft", [1024, 512])
+@pytest.mark.parametrize("n_fft", [1024, 512, 4096])
 def test_subwarp_register_fft_kernel(built, n_fft):
-    """n_fft = 1024 / 512 run the frames_sub kernel (16 / 8 lanes per frame, 2 / 4 frames per warp):
-    the same cases the 2048 kernel is put through, plus agreement with the generic kernel."""
+    """n_fft = 1024 / 512 run the frames_sub kernel (16 / 8 lanes per frame, 2 / 4 frames per warp) and
+    n_fft = 4096 the two-pass frames_fast_4096 kernel (even / odd bins): the same cases the 2048 kernel
+    is put through, plus agreement with the generic kernel."""
     import torch
 
     hl = built
