@@ -245,6 +245,35 @@ class FeatureExtractor:
                                            C.c_void_p(stream)))
         return out
 
+    def extract_pooled_device(self, waves, *, mfcc=True, chroma=False):
+        """Only the time-pooled columns of a device-resident batch ([R] extract_all_features /
+        extract_flattened_features keep nothing else): ``pooled`` (B, 2*n_mels + 2*n_mfcc + 10 [+ 24])
+        and ``status`` (B,).  power_to_db, the DCT and np.mean / np.std over frames run in one kernel;
+        the (B, n_mels, T) / (B, n_mfcc, T) arrays are never materialised."""
+        import torch
+
+        waves = self._as_cuda_batch(waves)
+        B, n = waves.shape
+        T = self.num_frames(n)
+        dev = waves.device
+        mfcc = bool(mfcc) and self.n_mfcc > 0
+        new = lambda shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=dev)
+        po = new((B, self.pooled_width(mfcc, bool(chroma))))
+        st, sta, cm = new((B, 5, T)), new((B,), torch.int32), new((B,))
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        ch = tu = work = None
+        wbytes = 0
+        if chroma:
+            wbytes = int(lib.hlmc_chroma_workspace_bytes(self._plan, B, n))
+            if wbytes < 0:
+                _check(wbytes)
+            ch, tu, work = new((B, 12, T)), new((B,)), new((max(wbytes, 1),), torch.uint8)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(lib.hlmc_extract_pooled_device(self._plan, ptr(waves), B, n, _row_pitch(waves), ptr(po), int(mfcc),
+                                              int(bool(chroma)), ptr(st), ptr(sta), ptr(cm), ptr(ch), ptr(tu),
+                                              ptr(work), wbytes, C.c_void_p(stream)))
+        return {"pooled": po, "status": sta}
+
     def melspectrogram_device(self, waves, *, stats=False):
         import torch
 

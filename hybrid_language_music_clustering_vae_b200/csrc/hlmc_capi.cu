@@ -724,16 +724,22 @@ int64_t hlmc_chroma_workspace_bytes(hlmc_plan* plan, int64_t B, int64_t n) {
                      (size_t)B * T * plan->cand_per_frame * sizeof(float2));
 }
 
+// d_pooled with d_logmel == NULL selects the fused path: dB, DCT and time pooling in one kernel, the
+// (B, n_mels, T) / (B, n_mfcc, T) arrays are never written.
 static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
                                float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
                                float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
-                               int64_t work_bytes, void* stream, float* d_melscr) {
+                               int64_t work_bytes, void* stream, float* d_melscr,
+                               float* d_pooled = nullptr, int pool_mfcc = 0, int pool_chroma = 0) {
     int64_t T;
     int rc = check_batch(plan, d_wave, B, n, pitch, &T);
     if (rc != HLMC_OK) return rc;
     if (B == 0) return HLMC_OK;
-    if (!d_logmel || !d_clipmax) return fail(HLMC_ERR_PARAM, "d_logmel and d_clipmax are required");
-    if (d_mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
+    const bool fused = (d_pooled != nullptr && d_logmel == nullptr);
+    if ((!fused && !d_logmel) || !d_clipmax) return fail(HLMC_ERR_PARAM, "d_logmel and d_clipmax are required");
+    if (fused && !d_stats) return fail(HLMC_ERR_PARAM, "the pooled path needs a (B, 5, T) d_stats buffer");
+    if (fused && pool_chroma && !d_chroma) return fail(HLMC_ERR_PARAM, "pooled chroma columns need d_chroma");
+    if ((d_mfcc || (fused && pool_mfcc)) && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
     CK(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // chroma: piptrack candidates come out of the same pass as the other features
@@ -772,18 +778,29 @@ static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, 
     d.dct_t = plan->d_dct_t; d.B = (int)B; d.n_mels = plan->p.n_mels; d.n_mfcc = plan->p.n_mfcc;
     d.ncp = plan->ncp; d.T = (int)T; d.ref_mode = plan->p.ref_mode; d.ref_value = plan->p.ref_value;
     d.amin = plan->p.amin; d.top_db = plan->p.top_db;
-    CK(launch_db_dct(d, st));
+    auto run_chroma = [&]() -> int {
+        CK(launch_tuning(cand, cand_count, (int)T, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
+        FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
+        ChromaArgs ca{tuning_idx, plan->d_chroma_fb, d_chroma};
+        CK(launch_chroma_fast(a, ca, plan->d_fast, plan->ft, plan->num_sms, st));
+        return HLMC_OK;
+    };
+    if (fused) {
+        if (d_chroma) { rc = run_chroma(); if (rc != HLMC_OK) return rc; }     // its pooled columns come from (B, 12, T)
+        PoolArgs pa{};
+        pa.stats = d_stats; pa.chroma = pool_chroma ? d_chroma : nullptr; pa.n_chroma = pool_chroma ? kChroma : 0;
+        pa.with_mfcc = pool_mfcc ? 1 : 0; pa.pooled = d_pooled;
+        pa.pooled_w = 2 * d.n_mels + 2 * (pool_mfcc ? d.n_mfcc : 0) + 10 + 2 * pa.n_chroma;
+        CK(launch_db_pool(d, pa, plan->num_sms, st));
+    } else {
+        CK(launch_db_dct(d, st));
+    }
     if (plan->timing) {
         CK(cudaEventRecord(ev3[2], st));
         for (auto& e : ev3) plan->ev.push_back(e);
     }
     if (own_scr) CK(cudaFreeAsync(d_melscr, st));
-    if (d_chroma) {
-        CK(launch_tuning(cand, cand_count, (int)T, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
-        FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
-        ChromaArgs ca{tuning_idx, plan->d_chroma_fb, d_chroma};
-        CK(launch_chroma_fast(a, ca, plan->d_fast, plan->ft, plan->num_sms, st));
-    }
+    if (d_chroma && !fused) { rc = run_chroma(); if (rc != HLMC_OK) return rc; }
     return HLMC_OK;
 }
 
@@ -800,6 +817,16 @@ int hlmc_extract_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t
                         float* d_clipmax, void* stream) {
     return extract_device_impl(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax,
                                nullptr, nullptr, nullptr, 0, stream, nullptr);
+}
+
+int hlmc_extract_pooled_device(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                               float* d_pooled, int with_mfcc, int with_chroma, float* d_stats, int32_t* d_status,
+                               float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
+                               int64_t work_bytes, void* stream) {
+    if (!d_pooled) return fail(HLMC_ERR_PARAM, "d_pooled is required");
+    return extract_device_impl(plan, d_wave, B, n, pitch, nullptr, nullptr, d_stats, d_status, d_clipmax,
+                               with_chroma ? d_chroma : nullptr, with_chroma ? d_tuning : nullptr, d_work, work_bytes,
+                               stream, nullptr, d_pooled, with_mfcc, with_chroma);
 }
 
 int hlmc_plan_set_timing(hlmc_plan* plan, int enable) {
@@ -1006,18 +1033,23 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
                                      (size_t)c, s.stream));
         }
         plan->last_h2d += c * n_valid * (int64_t)esz;
-        rc = extract_device_impl(plan, s.d_wave, c, n, dp, s.d_logmel, want_mfcc ? s.d_mfcc : nullptr,
+        // only pooled columns wanted: dB + DCT + pooling fused, no log-mel / MFCC arrays in HBM
+        const bool fused = io->pooled && !io->logmel && !io->mfcc;
+        rc = extract_device_impl(plan, s.d_wave, c, n, dp, fused ? nullptr : s.d_logmel,
+                                 (want_mfcc && !fused) ? s.d_mfcc : nullptr,
                                  s.d_stats, s.d_status, s.d_clipmax, want_chroma ? s.d_chroma : nullptr,
                                  want_chroma ? s.d_tuning : nullptr, want_chroma ? s.d_cwork : nullptr,
-                                 chroma_ws, s.stream, s.d_melscr);
+                                 chroma_ws, s.stream, s.d_melscr, fused ? s.d_pooled : nullptr, want_mfcc ? 1 : 0,
+                                 pool_chroma ? 1 : 0);
         if (rc != HLMC_OK) return rc;
         auto d2h = [&](void* dst, const void* srcd, size_t bytes) -> cudaError_t {
             plan->last_d2h += (int64_t)bytes;
             return cudaMemcpyAsync(dst, srcd, bytes, cudaMemcpyDeviceToHost, s.stream);
         };
         if (io->pooled) {
-            CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, pool_chroma ? s.d_chroma : nullptr,
-                           c, nm, nc, (int)T, s.d_pooled, s.stream));
+            if (!fused)
+                CK(launch_pool(s.d_logmel, want_mfcc ? s.d_mfcc : nullptr, s.d_stats, pool_chroma ? s.d_chroma : nullptr,
+                               c, nm, nc, (int)T, s.d_pooled, s.stream));
             CK(d2h(io->pooled + done * pooled_w, s.d_pooled, (size_t)c * pooled_w * 4));
         }
         if (io->logmel) CK(d2h(io->logmel + done * nm * T, s.d_logmel, (size_t)c * nm * T * 4));

@@ -93,6 +93,16 @@ struct DbArgs {
     int ref_mode; float ref_value, amin, top_db;
 };
 
+// Extra arguments of the fused dB + DCT + time-pooling kernel (db_pool).
+struct PoolArgs {
+    const float* stats;     // (B, 5, T), written by the frames kernel
+    const float* chroma;    // (B, n_chroma, T) or NULL
+    int n_chroma;           // 0 or 12
+    int with_mfcc;          // pool the MFCC rows too
+    float* pooled;          // (B, pooled_w)
+    int pooled_w;           // 2*n_mels + 2*n_mfcc*with_mfcc + 10 + 2*n_chroma
+};
+
 // launchers (all asynchronous on `stream`; return cudaError_t)
 cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                int num_sms, cudaStream_t stream);
@@ -108,6 +118,7 @@ cudaError_t launch_tuning(const float2* cand, const int* cand_count, int T, int 
                           const double* d_edges, float* tuning, int* tuning_idx, cudaStream_t stream);
 cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, cudaStream_t stream);
 cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream);
+cudaError_t launch_db_pool(const DbArgs& a, const PoolArgs& pa, int num_sms, cudaStream_t stream);
 cudaError_t launch_rowmax(const float* in, unsigned int* clipmax, long long B, long long per_clip,
                           cudaStream_t stream);
 cudaError_t launch_power_to_db(const float* in, float* out, const unsigned int* clipmax, long long B,

@@ -2008,6 +2008,219 @@ static cudaError_t launch_db_nc(const DbArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// power_to_db + DCT-II + time pooling in one kernel: what 1_preprocessing.py keeps of a clip
+// is np.mean / np.std over frames of every log-mel band, MFCC and statistic ([R] src/1_preprocessing.py:
+// 115-124), so when the caller does not ask for the (B, n_mels, T) / (B, n_mfcc, T) arrays they are never
+// written to HBM.  One CTA per clip, frames in tiles of 128: phase 1 is db_dct's arithmetic (one thread per
+// frame) into a shared-memory tile, phase 2 turns the tile by 90 degrees (one thread per band / coefficient):
+// mean and squared deviations of the tile's frames in two passes over shared memory, tiles combined with
+// Chan's update (a constant row has exactly zero variance; no cancellation however far the mean is from 0).
+// The 5 statistics rows and the 24 chroma rows are pooled from HBM with pool_kernel's two-pass arithmetic.
+// ---------------------------------------------------------------------------
+// Threads per CTA = frames per tile, chosen at launch so that the clip's T frames fill the tiles evenly
+// (T = 130 -> one tile of 160; T = 1292 -> six tiles of 224), between 128 and 256.
+constexpr int kPoolMinThreads = 128, kPoolMaxThreads = 256;
+constexpr int kPoolRowsPerThread = kMaxMelGroups * 32 / kPoolMinThreads;   // n_mels <= 256
+static int pool_threads(int T) {
+    const int tiles = (T + kPoolMaxThreads - 1) / kPoolMaxThreads;
+    int nt = (((T + tiles - 1) / tiles) + 31) & ~31;
+    if (nt < kPoolMinThreads) nt = kPoolMinThreads;
+    return nt;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kPoolMaxThreads) db_pool(const DbArgs a, const PoolArgs pa) {
+    extern __shared__ __align__(16) float sP[];
+    constexpr int H = NC / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x;                      // = frames per tile
+    const int half = a.n_mels >> 1;
+    const int rows = (a.n_mels + 1) >> 1;
+    const int TS = a.n_mels + 1, MS = NC + 1;
+    float* sD = sP;
+    float* tile = sD + ((rows * NC + 3) & ~3);
+    float* tileM = tile + NT * TS;
+    if constexpr (NC > 0) {
+        for (int i = tid; i < rows * NC; i += NT) {
+            const int n = i / NC, j = i - n * NC;
+            const int c = (j < H) ? 2 * j : 2 * (j - H) + 1;
+            sD[i] = a.dct_t[n * NC + c];
+        }
+    }
+    __syncthreads();
+    const bool same_amin = (a.amin == 1e-10f);
+    const bool vec = (a.n_mels & 7) == 0;
+    const float invT = 1.0f / float(a.T);
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const float pmax = __uint_as_float(a.clipmax[b]);
+        const float maxa = db10(fmaxf(a.amin, pmax));
+        const float ref_db = (a.ref_mode == 1) ? maxa : db10(fmaxf(a.amin, fabsf(a.ref_value)));
+        const float floor_db = (a.top_db >= 0.0f) ? (maxa - ref_db) - a.top_db : -CUDART_INF_F;
+        const float floor_m = db10(fmaxf(1e-10f, pmax)) - 80.0f;
+        float mean_m[kPoolRowsPerThread], m2_m[kPoolRowsPerThread];       // running mean / sum of squared deviations
+#pragma unroll
+        for (int r = 0; r < kPoolRowsPerThread; ++r) { mean_m[r] = 0.f; m2_m[r] = 0.f; }
+        float mean_c = 0.f, m2_c = 0.f;
+        // one tile's column: two passes over shared memory, then Chan's parallel update of (mean, M2)
+        auto absorb = [&](const float* col, int stride, int nt, int t0, float& mean, float& m2) {
+            float sum = 0.0f;
+            for (int f = 0; f < nt; ++f) sum += col[f * stride];
+            const float tmean = sum / float(nt);
+            float q = 0.0f;
+            for (int f = 0; f < nt; ++f) { const float d = col[f * stride] - tmean; q = fmaf(d, d, q); }
+            if (t0 == 0) { mean = tmean; m2 = q; }
+            else {
+                const float na = float(t0), nb = float(nt), delta = tmean - mean;
+                mean = fmaf(delta, nb / (na + nb), mean);
+                m2 += q + delta * delta * (na * nb / (na + nb));
+            }
+        };
+        for (int t0 = 0; t0 < a.T; t0 += NT) {
+            const int t = t0 + tid;
+            if (t < a.T) {
+                // ---- phase 1: this thread's frame: dB of every band into the tile, DCT in registers
+                const float* row = a.mel_in + ((size_t)b * a.T + t) * a.n_mels;
+                float* trow = tile + tid * TS;
+                float2 acc[NC > 0 ? H : 1];
+#pragma unroll
+                for (int c = 0; c < H; ++c) acc[c] = make_float2(0.f, 0.f);
+                auto to_db = [&](float p, int m) -> float {
+                    const float adb = db10(fmaxf(a.amin, p));
+                    trow[m] = fmaxf(adb - ref_db, floor_db);
+                    const float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
+                    return fmaxf(x, floor_m);
+                };
+                constexpr int MB = 4;
+                for (int n0 = 0; n0 < half; n0 += MB) {
+                    float lo[MB], hi[MB];
+                    if (vec) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(row + n0));
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(row + a.n_mels - MB - n0));
+                        lo[0] = u.x; lo[1] = u.y; lo[2] = u.z; lo[3] = u.w;
+                        hi[0] = v.w; hi[1] = v.z; hi[2] = v.y; hi[3] = v.x;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < MB; ++j) {
+                            const bool in = n0 + j < half;
+                            lo[j] = in ? row[n0 + j] : 0.0f;
+                            hi[j] = in ? row[a.n_mels - 1 - n0 - j] : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < MB; ++j) {
+                        const int n = n0 + j;
+                        if (n >= half) break;
+                        const float xl = to_db(lo[j], n), xh = to_db(hi[j], a.n_mels - 1 - n);
+                        if constexpr (NC > 0) {
+                            const float2 sf = make_float2(xl + xh, xl + xh), df = make_float2(xl - xh, xl - xh);
+                            const float4* d4 = reinterpret_cast<const float4*>(sD + n * NC);
+#pragma unroll
+                            for (int c = 0; c < H / 4; ++c) {
+                                const float4 e = d4[c], o = d4[H / 4 + c];
+                                acc[2 * c] = __ffma2_rn(make_float2(e.x, e.y), sf, acc[2 * c]);
+                                acc[2 * c + 1] = __ffma2_rn(make_float2(e.z, e.w), sf, acc[2 * c + 1]);
+                                acc[H / 2 + 2 * c] = __ffma2_rn(make_float2(o.x, o.y), df, acc[H / 2 + 2 * c]);
+                                acc[H / 2 + 2 * c + 1] = __ffma2_rn(make_float2(o.z, o.w), df, acc[H / 2 + 2 * c + 1]);
+                            }
+                        }
+                    }
+                }
+                if (a.n_mels & 1) {
+                    const float x = to_db(row[half], half);
+                    if constexpr (NC > 0) {
+#pragma unroll
+                        for (int c = 0; c < H / 2; ++c)
+                            acc[c] = __ffma2_rn(make_float2(sD[half * NC + 2 * c], sD[half * NC + 2 * c + 1]),
+                                                make_float2(x, x), acc[c]);
+                    }
+                }
+                if constexpr (NC > 0) {
+                    float* mrow = tileM + tid * MS;
+#pragma unroll
+                    for (int j = 0; j < H; ++j) {
+                        mrow[2 * j] = (j & 1) ? acc[j >> 1].y : acc[j >> 1].x;
+                        mrow[2 * j + 1] = (j & 1) ? acc[H / 2 + (j >> 1)].y : acc[H / 2 + (j >> 1)].x;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase 2: one thread per band / coefficient walks the tile's frames
+            const int nt = (a.T - t0 < NT) ? a.T - t0 : NT;
+#pragma unroll
+            for (int r = 0; r < kPoolRowsPerThread; ++r) {
+                const int m = tid + r * NT;
+                if (m < a.n_mels) absorb(tile + m, TS, nt, t0, mean_m[r], m2_m[r]);
+            }
+            if (NC > 0 && pa.with_mfcc && tid < a.n_mfcc) absorb(tileM + tid, MS, nt, t0, mean_c, m2_c);
+            __syncthreads();
+        }
+        // ---- the clip's pooled row: [mel mean | mel std | mfcc mean | mfcc std | 5 x (mean, std) | chroma mean | chroma std]
+        float* out = pa.pooled + (size_t)b * pa.pooled_w;
+        const int nc_out = pa.with_mfcc ? a.n_mfcc : 0;
+#pragma unroll
+        for (int r = 0; r < kPoolRowsPerThread; ++r) {
+            const int m = tid + r * NT;
+            if (m < a.n_mels) {
+                out[m] = mean_m[r];
+                out[a.n_mels + m] = sqrtf(m2_m[r] * invT);
+            }
+        }
+        if (NC > 0 && pa.with_mfcc && tid < a.n_mfcc) {
+            out[2 * a.n_mels + tid] = mean_c;
+            out[2 * a.n_mels + a.n_mfcc + tid] = sqrtf(m2_c * invT);
+        }
+        const int base = 2 * a.n_mels + 2 * nc_out;
+        for (int r = warp; r < 5 + pa.n_chroma; r += NT / 32) {
+            const float* src = (r < 5) ? pa.stats + ((size_t)b * 5 + r) * a.T
+                                       : pa.chroma + ((size_t)b * pa.n_chroma + (r - 5)) * a.T;
+            float sum = 0.0f;
+            for (int i = lane; i < a.T; i += 32) sum += src[i];
+            sum = warp_sum(sum);
+            const float mean = sum / float(a.T);
+            float var = 0.0f;
+            for (int i = lane; i < a.T; i += 32) { const float d = src[i] - mean; var = fmaf(d, d, var); }
+            var = warp_sum(var);
+            if (lane == 0) {
+                const int o_mean = (r < 5) ? base + 2 * r : base + 10 + (r - 5);
+                const int o_std = (r < 5) ? o_mean + 1 : o_mean + pa.n_chroma;
+                out[o_mean] = mean;
+                out[o_std] = sqrtf(var / float(a.T));
+            }
+        }
+    }
+}
+
+template <int NC>
+static cudaError_t launch_db_pool_nc(const DbArgs& a, const PoolArgs& pa, int num_sms, cudaStream_t stream) {
+    if (a.B <= 0 || a.T <= 0) return cudaSuccess;
+    const int rows = (a.n_mels + 1) / 2;
+    const int nt = pool_threads(a.T);
+    const int smem = (((rows * NC + 3) & ~3) + nt * (a.n_mels + 1) + nt * (NC + 1)) * 4;
+    cudaError_t e = cudaFuncSetAttribute(db_pool<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const int per_sm = (227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1;
+    long long grid = (long long)num_sms * per_sm;
+    if (grid > a.B) grid = a.B;
+    db_pool<NC><<<(unsigned)grid, nt, smem, stream>>>(a, pa);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_db_pool(const DbArgs& a, const PoolArgs& pa, int num_sms, cudaStream_t stream) {
+    if (!pa.with_mfcc || a.n_mfcc <= 0) return launch_db_pool_nc<0>(a, pa, num_sms, stream);
+    switch (a.ncp) {
+        case 8: return launch_db_pool_nc<8>(a, pa, num_sms, stream);
+        case 16: return launch_db_pool_nc<16>(a, pa, num_sms, stream);
+        case 24: return launch_db_pool_nc<24>(a, pa, num_sms, stream);
+        case 32: return launch_db_pool_nc<32>(a, pa, num_sms, stream);
+        case 40: return launch_db_pool_nc<40>(a, pa, num_sms, stream);
+        case 64: return launch_db_pool_nc<64>(a, pa, num_sms, stream);
+        case 128: return launch_db_pool_nc<128>(a, pa, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream) {
     if (a.mfcc == nullptr || a.n_mfcc <= 0) return launch_db_nc<0>(a, stream);
     switch (a.ncp) {

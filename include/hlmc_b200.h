@@ -149,6 +149,18 @@ int hlmc_extract_device_ex(hlmc_plan *plan, const float *d_wave, int64_t B, int6
                            int32_t *d_status, float *d_clipmax, float *d_chroma, float *d_tuning,
                            void *d_work, int64_t work_bytes, void *stream);
 
+/* Only what 1_preprocessing.py keeps of a clip ([R] src/1_preprocessing.py:115-129, extract_all_features;
+ * src/1_preprocessing_advanced.py:144-156 with with_mfcc = 0): np.mean / np.std over frames of every
+ * log-mel band, MFCC, statistic and chroma bin, in the scripts' column order
+ *   d_pooled : (B, 2*n_mels + 2*n_mfcc*with_mfcc + 10 + 24*with_chroma) float32
+ * power_to_db, the DCT and the pooling run in one kernel: the (B, n_mels, T) and (B, n_mfcc, T) arrays are
+ * never written.  d_stats (B, 5, T) and d_clipmax (B) are required scratch; d_chroma (B, 12, T), d_tuning (B)
+ * and d_work as for hlmc_extract_device_ex when with_chroma != 0.  */
+int hlmc_extract_pooled_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t n,
+                               int64_t pitch, float *d_pooled, int with_mfcc, int with_chroma,
+                               float *d_stats, int32_t *d_status, float *d_clipmax, float *d_chroma,
+                               float *d_tuning, void *d_work, int64_t work_bytes, void *stream);
+
 /* Per-kernel timing of hlmc_extract_device for the roofline report: when
  * enabled, CUDA events are recorded on the launching stream around the frames
  * kernel and around the dB+DCT kernel.  hlmc_plan_read_timing synchronises on

@@ -396,8 +396,10 @@ def test_chroma_stft_and_tuning_on_device(built):
     # the host pipeline produces the same chroma (chunked, overlapped copies)
     hp = ex.extract_host(y, chroma=True, pooled=True, chunk_clips=7)
     assert np.array_equal(hp["chroma"], ch) and np.array_equal(hp["tuning"], tu) and np.array_equal(hp["pooled"], po)
+    # pooled columns only: the fused dB + DCT + pooling kernel (one-pass shifted sums instead of two passes)
     hp2 = ex.extract_host(y, logmel=False, mfcc=False, stats=False, pooled=True, chroma="pooled")
-    assert "chroma" not in hp2 and np.array_equal(hp2["pooled"], po)
+    assert "chroma" not in hp2 and np.abs(hp2["pooled"] - po).max() <= 2e-5 * np.abs(po).max()
+    assert np.array_equal(hp2["pooled"][:, 336:], po[:, 336:])          # statistics + chroma columns: same arithmetic
     c1 = hl.feature.chroma_stft(y=y[3], sr=SR, n_fft=2048, hop_length=512)
     assert c1.shape == (12, 130) and np.array_equal(c1, ch[3])
     with pytest.raises(hl.UnsupportedError):
@@ -495,3 +497,34 @@ def test_subwarp_register_fft_kernel(built, n_fft):
     bad[3, 100] = float("nan")
     ex.force_generic(False)
     assert ex.extract_device(bad)["status"].cpu().tolist() == [0, 0, 0, 1] + [0] * 60
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(n_mels=40, n_mfcc=13), dict(n_mels=96, n_mfcc=0), dict(n_mels=33, n_mfcc=8),
+                                dict(n_fft=1024, hop_length=256), dict(ref=1.0, top_db=None)])
+def test_fused_pooled_only_path(built, kw):
+    """hlmc_extract_pooled_device never writes log-mel / MFCC to HBM; its columns equal
+    np.mean / np.std over frames of the full outputs (float32 accumulation, so 1e-5 of the column scale)."""
+    import torch
+
+    hl = built
+    ex = hl.FeatureExtractor(**dict(dict(ref=np.max, n_mfcc=40), **kw))
+    for n in (22050, 300, 200000):          # 44 frames, 1 frame, 391 frames (several 128-frame tiles)
+        y = hl.synth.synth_batch(9, n, seed=n)
+        yd = torch.from_numpy(y).cuda()
+        full = {k: v.cpu().numpy().astype(np.float64) for k, v in ex.extract_device(yd).items()}
+        got = ex.extract_pooled_device(yd)
+        po = got["pooled"].cpu().numpy()
+        parts = [full["logmel"].mean(-1), full["logmel"].std(-1)]
+        if ex.n_mfcc > 0:
+            parts += [full["mfcc"].mean(-1), full["mfcc"].std(-1)]
+        st = full["stats"]
+        parts.append(np.stack([st.mean(-1), st.std(-1)], axis=-1).reshape(len(y), 10))
+        want = np.concatenate(parts, axis=1)
+        assert po.shape == want.shape == (9, ex.pooled_width(ex.n_mfcc > 0))
+        scale = np.maximum(np.abs(want).max(axis=0, keepdims=True), 1.0)
+        assert np.abs(po - want).max() <= 2e-4 * scale.max() and (np.abs(po - want) / scale).max() <= 5e-5, kw
+        assert np.array_equal(got["status"].cpu().numpy(), full["status"].astype(np.int32))
+    # constant rows pool to exactly zero variance (all-zero clip: every band sits on the dB floor)
+    z = ex.extract_pooled_device(torch.zeros((2, 22050), device="cuda"))["pooled"].cpu().numpy()
+    nm = ex.n_mels
+    assert np.all(z[:, nm:2 * nm] == 0.0)
