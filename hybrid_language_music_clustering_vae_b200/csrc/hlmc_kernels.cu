@@ -160,14 +160,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // warp-uniform but only known at run time.  Steps are taken in straight-line chunks of 4, 2 and 1 so
 // that all shared-memory loads of a chunk are in flight before its first multiply-add (a step-by-step
 // loop pays the full load latency 26 times per frame; ncu showed it as the top short-scoreboard stall).
-template <int CH>
+template <int CH, int WS>
 __device__ __forceinline__ void mel_chunk(const float4* __restrict__ wp, const float* __restrict__ pp,
                                           float2& a01, float2& a23) {
     float4 w[CH];
     float2 p01[CH], p23[CH];
 #pragma unroll
     for (int s = 0; s < CH; ++s) {
-        w[s] = wp[32 * s];
+        w[s] = wp[WS * s];
         p01[s] = make_float2(pp[4 * s + 0], pp[4 * s + 1]);
         p23[s] = make_float2(pp[4 * s + 2], pp[4 * s + 3]);
     }
@@ -177,11 +177,13 @@ __device__ __forceinline__ void mel_chunk(const float4* __restrict__ wp, const f
         a23 = __ffma2_rn(make_float2(w[s].z, w[s].w), p23[s], a23);
     }
 }
+// WS = float4 stride between a lane's consecutive steps (lanes per filter round: 32, or L in frames_sub)
+template <int WS = 32>
 __device__ __forceinline__ void mel_steps(int n4, const float4* __restrict__ wp, const float* __restrict__ pp,
                                           float2& a01, float2& a23) {
-    for (; n4 >= 4; n4 -= 4, wp += 4 * 32, pp += 16) mel_chunk<4>(wp, pp, a01, a23);
-    if (n4 & 2) { mel_chunk<2>(wp, pp, a01, a23); wp += 2 * 32; pp += 8; }
-    if (n4 & 1) mel_chunk<1>(wp, pp, a01, a23);
+    for (; n4 >= 4; n4 -= 4, wp += 4 * WS, pp += 16) mel_chunk<4, WS>(wp, pp, a01, a23);
+    if (n4 & 2) { mel_chunk<2, WS>(wp, pp, a01, a23); wp += 2 * WS; pp += 8; }
+    if (n4 & 1) mel_chunk<1, WS>(wp, pp, a01, a23);
 }
 
 struct WarpState {
@@ -1187,34 +1189,42 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
             constexpr int CH = G::NFFT / L;           // contiguous samples per lane
             int zc = 0;
             float prev = sample_edge(clip, a.n, fs + lg * CH - 1);
-            for (int i = 0; i < CH; ++i) {
-                const int sidx = fs + lg * CH + i;
-                sc[lg * CH + i] = sample_padded(clip, a.n, sidx, a.pad_mode);
-                const float e = sample_edge(clip, a.n, sidx);
-                if ((lg * CH + i) > 0) zc += ((e < -zthr) != (prev < -zthr)) ? 1 : 0;
-                prev = e;
+            for (int i0 = 0; i0 < CH; i0 += 8) {
+                float ve[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ve[u] = sample_edge(clip, a.n, fs + lg * CH + i0 + u);   // 8 loads in flight
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u, sidx = fs + lg * CH + i;
+                    const bool inside = (sidx >= 0) && (sidx < a.n);
+                    sc[lg * CH + i] = inside ? ve[u] : ((a.pad_mode == 0) ? 0.0f : (a.pad_mode == 1) ? __ldg(clip + reflect_index(sidx, a.n)) : ve[u]);
+                    if ((lg * CH + i) > 0) zc += ((ve[u] < -zthr) != (prev < -zthr)) ? 1 : 0;
+                    prev = ve[u];
+                }
             }
             zc_edge = group_sum_i<L>(zc);
             off = 0;
             __syncwarp();
         }
 
-        float vr[64], vi[64];
-        float ss = 0.0f;
+        float2 v[32];                                   // packed FP32: one complex value per register pair
+        float ss;
         unsigned za = 0u, zb = 0u;
         {
             const float2* xp = reinterpret_cast<const float2*>(sc + off);
+            const float2 zt = make_float2(zthr, zthr);
+            float2 ss2 = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float2 x = xp[lg + L * j];
                 const float2 w = s_win[lg + L * j];
-                ss = fmaf(x.x, x.x, ss);
-                ss = fmaf(x.y, x.y, ss);
-                za = __funnelshift_l(__float_as_uint(x.x + zthr), za, 1);
-                zb = __funnelshift_l(__float_as_uint(x.y + zthr), zb, 1);
-                vr[j] = x.x * w.x;
-                vi[j] = x.y * w.y;
+                ss2 = __ffma2_rn(x, x, ss2);
+                const float2 xt = __fadd2_rn(x, zt);
+                za = __funnelshift_l(__float_as_uint(xt.x), za, 1);
+                zb = __funnelshift_l(__float_as_uint(xt.y), zb, 1);
+                v[j] = __fmul2_rn(x, w);
             }
+            ss = ss2.x + ss2.y;
         }
         int zc;
         {
@@ -1229,77 +1239,74 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
         __syncwarp();
 
         // pass 1: 32-point FFT over n1 (z[lg + L*n1]); twiddle W_M^(lg*k1)
-        fftreg::fft_dif<32>(vr, vi);
+        fftreg2::fft_dif<32>(v);
 #pragma unroll
         for (int k1 = 1; k1 < 32; ++k1) {
             const float2 w = s_tw1[(k1 - 1) * L + lg];
             const int p = pos32(k1);
-            const float xr = vr[p], xi = vi[p];
-            vr[p] = fmaf(xr, w.x, -(xi * w.y));
-            vi[p] = fmaf(xr, w.y, xi * w.x);
+            v[p] = fftreg2::cmul(v[p], w.x, w.y);
         }
         // transpose inside the group: lane lg then owns columns k1 = lg + L*c
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) sc2[lg * 33 + k1] = make_float2(vr[pos32(k1)], vi[pos32(k1)]);
+        for (int k1 = 0; k1 < 32; ++k1) sc2[lg * 33 + k1] = v[pos32(k1)];
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < G::C; ++c)
 #pragma unroll
-            for (int n2 = 0; n2 < L; ++n2) {
-                const float2 v = sc2[n2 * 33 + lg + L * c];
-                vr[c * L + n2] = v.x; vi[c * L + n2] = v.y;
-            }
+            for (int n2 = 0; n2 < L; ++n2) v[c * L + n2] = sc2[n2 * 33 + lg + L * c];
         __syncwarp();
         // pass 2: an L-point FFT per column; bin k = (lg + L*c) + 32*k2 sits at c*L + fft_pos<L>(k2)
         if constexpr (L == 16) {
-            fftreg::fft_dif<16, 0>(vr, vi);
-            fftreg::fft_dif<16, 16>(vr, vi);
+            fftreg2::fft_dif<16, 0>(v);
+            fftreg2::fft_dif<16, 16>(v);
         } else {
-            fftreg::fft_dif<8, 0>(vr, vi);
-            fftreg::fft_dif<8, 8>(vr, vi);
-            fftreg::fft_dif<8, 16>(vr, vi);
-            fftreg::fft_dif<8, 24>(vr, vi);
+            fftreg2::fft_dif<8, 0>(v);
+            fftreg2::fft_dif<8, 8>(v);
+            fftreg2::fft_dif<8, 16>(v);
+            fftreg2::fft_dif<8, 24>(v);
         }
         // regroup (layout p(k) = k + k/16): lane lg owns bins [16*lg, 16*lg+16) and mirrors M-k
 #pragma unroll
         for (int c = 0; c < G::C; ++c)
 #pragma unroll
             for (int k2 = 0; k2 < L; ++k2) {
-                constexpr int dummy = 0; (void)dummy;
                 const int src = c * L + fftreg::fft_pos<L>(k2);
-                sc2[zw_base + (L * c + ((L * c) >> 4)) + 34 * k2] = make_float2(vr[src], vi[src]);
+                sc2[zw_base + (L * c + ((L * c) >> 4)) + 34 * k2] = v[src];
             }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const float2 v = sc2[zlo_base + i]; vr[i] = v.x; vi[i] = v.y; }
-        { const float2 v = sc2[zhi0]; vr[16] = v.x; vi[16] = v.y; }
+        for (int i = 0; i < 16; ++i) v[i] = sc2[zlo_base + i];
+        v[16] = sc2[zhi0];
 #pragma unroll
-        for (int i = 1; i < 16; ++i) { const float2 v = sc2[zhi_base - i]; vr[16 + i] = v.x; vi[16 + i] = v.y; }
+        for (int i = 1; i < 16; ++i) v[16 + i] = sc2[zhi_base - i];
         const float2 emid = sc2[17 * L];
         __syncwarp();
 
-        // real-FFT split, |X|^2, |X|, moments
-        float m0l = 0.f, m1l = 0.f, m0h = 0.f, m1h = 0.f;
+        // real-FFT split, |X|^2, |X|, moments of |X| about the centres of the lane's two runs
+        float2 P[16], S[16];
+        float2 M0 = make_float2(0.f, 0.f), M1 = M0, M2 = M0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float2 w = s_tw2[i * L + lg];
-            const float ex = vr[i] + vr[16 + i], ey = vi[i] - vi[16 + i];
-            const float dx = vr[i] - vr[16 + i], dy = vi[i] + vi[16 + i];
-            const float tx = fmaf(w.x, dx, -(w.y * dy));
-            const float ty = fmaf(w.x, dy, w.y * dx);
-            const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
-            const float pk = fmaf(ar, ar, ai * ai);
-            const float pm = fmaf(br, br, bi * bi);
-            const float sk = fast_sqrt(pk), sm = fast_sqrt(pm);
-            vr[i] = pk; vr[16 + i] = pm; vi[i] = sk; vi[16 + i] = sm;
-            const float d = float(i) - 7.5f;
-            m0l += sk; m1l = fmaf(d, sk, m1l);
-            m0h += sm; m1h = fmaf(-d, sm, m1h);
+            const float2 za_ = v[i], zb_ = v[16 + i];
+            const float2 e = __fadd2_rn(za_, make_float2(zb_.x, -zb_.y));
+            const float2 d = __fadd2_rn(za_, make_float2(-zb_.x, zb_.y));
+            const float2 tt = fftreg2::cmul(d, w.x, w.y);
+            const float2 xa = __fadd2_rn(e, tt), xb = __fadd2_rn(e, make_float2(-tt.x, -tt.y));
+            const float2 pw = make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
+            const float2 sq = make_float2(fast_sqrt(pw.x), fast_sqrt(pw.y));
+            P[i] = pw;
+            S[i] = sq;
+            const float dd = float(i) - 7.5f;
+            M0 = __fadd2_rn(M0, sq);
+            M1 = __ffma2_rn(make_float2(sq.x, -sq.y), make_float2(dd, dd), M1);
+            M2 = __ffma2_rn(sq, make_float2(dd * dd, dd * dd), M2);
         }
+        const float m0l = M0.x, m0h = M0.y, m1l = M1.x, m1h = M1.y, m2l = M2.x, m2h = M2.y;
         const float pmid = 4.0f * fmaf(emid.x, emid.x, emid.y * emid.y);
         const float smid = fast_sqrt(pmid);
 
-        // centroid / bandwidth
+        // centroid / bandwidth (moments about the run centres, as in frames_fast_2048)
         const float fM = float(G::M);
         const float kcl = 16.0f * lg + 7.5f;
         const float kch = fM - 16.0f * lg - 7.5f;
@@ -1310,16 +1317,10 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
         s1 = group_sum<L>(s1);
         const float denom = (s0 < 1.17549435e-38f) ? 1.0f : s0;
         const float cen = s1 / denom;
-        float q = 0.0f;
+        float q;
         {
-            const float cl = cen - 16.0f * lg;
-            const float ch = (fM - 16.0f * lg) - cen;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float dl = float(i) - cl, dh = ch - float(i);
-                q = fmaf(dl * vi[i], dl, q);
-                q = fmaf(dh * vi[16 + i], dh, q);
-            }
+            const float dl = kcl - cen, dh = kch - cen;
+            q = fmaf(dl, fmaf(dl, m0l, 2.0f * m1l), m2l) + fmaf(dh, fmaf(dh, m0h, 2.0f * m1h), m2h);
             if (lg == L - 1) { const float dm = 0.5f * fM - cen; q = fmaf(dm * dm, smid, q); }
             q = group_sum<L>(q);
         }
@@ -1351,12 +1352,12 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
             float cum = pl - m0l;
             int cnt = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { cum += vi[i]; cnt += (cum < thr) ? 1 : 0; }
+            for (int i = 0; i < 16; ++i) { cum += S[i].x; cnt += (cum < thr) ? 1 : 0; }
             const int cand_lo = 16 * lg + min(cnt, 15);
             cum = mid + (ph - m0h);
             cnt = 0;
 #pragma unroll
-            for (int i = 15; i >= 0; --i) { cum += vi[16 + i]; cnt += (cum < thr) ? 1 : 0; }
+            for (int i = 15; i >= 0; --i) { cum += S[i].y; cnt += (cum < thr) ? 1 : 0; }
             const int cand_hi = G::M - 16 * lg - (15 - min(cnt, 15));
             const int tl_lo = lo_mask ? (__ffs(lo_mask) - 1) : 0;
             const int tl_hi = hi_mask ? (31 - __clz(hi_mask)) : 0;
@@ -1370,12 +1371,12 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
 
         // power (or magnitude) spectrum -> padded scratch of the group
         {
-            const float* val = a.use_mag ? vi : vr;
+            const bool mag = a.use_mag != 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) scp[17 * lg + i] = val[i];
-            scp[17 * (G::ROWS - lg)] = val[16];
+            for (int i = 0; i < 16; ++i) scp[17 * lg + i] = mag ? S[i].x : P[i].x;
+            scp[17 * (G::ROWS - lg)] = mag ? S[0].y : P[0].y;
 #pragma unroll
-            for (int i = 1; i < 16; ++i) scp[17 * (G::ROWS - 1 - lg) + 16 - i] = val[16 + i];
+            for (int i = 1; i < 16; ++i) scp[17 * (G::ROWS - 1 - lg) + 16 - i] = mag ? S[i].y : P[i].y;
             if (lg == L - 1) scp[17 * L] = a.use_mag ? smid : pmid;
             scp[17 * lg + 16] = 0.0f;
             scp[17 * (G::ROWS - 1 - lg) + 16] = 0.0f;
@@ -1394,15 +1395,10 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
                 const int n4 = s_meta[r];
                 const float4* wq = reinterpret_cast<const float4*>(s_melw + s_meta[R + r]) + lg;
                 const float* pq = scp + s_meta[2 * R + r * L + lg];
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                for (int it = 0; it < n4; ++it, wq += L, pq += 4) {
-                    const float4 w = wq[0];
-                    a0 = fmaf(w.x, pq[0], a0);
-                    a1 = fmaf(w.y, pq[1], a1);
-                    a2 = fmaf(w.z, pq[2], a2);
-                    a3 = fmaf(w.w, pq[3], a3);
-                }
-                const float acc = (a0 + a2) + (a1 + a3);
+                float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
+                mel_steps<L>(n4, wq, pq, a01, a23);
+                a01 = __fadd2_rn(a01, a23);
+                const float acc = a01.x + a01.y;
                 const int m = L * r + lg;
                 if (live && m < a.n_mels) outb[(size_t)m * mstride] = acc;
                 if (live) wmax = fmaxf(wmax, acc);
