@@ -194,3 +194,18 @@ def test_chan_combination_of_shard_statistics(built):
     assert n == 101 and np.allclose(mean, ref.mean_) and np.allclose(m2 / n, ref.var_)
     sc = make_sklearn_scaler(n, mean, m2 / n)
     assert np.allclose(sc.transform(X), ref.transform(X))
+
+
+def test_numa_binding_helpers_are_safe_without_a_gpu(built):
+    """bench.py pins each rank next to its GPU before allocating pinned buffers; without a GPU (or without
+    sysfs NUMA information) the helper must change nothing and report False."""
+    sh = built.sharding
+    assert sh._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sh._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert sh.bind_to_gpu_numa_node(0) in (False, True)
+    import torch
+
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
