@@ -982,7 +982,11 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
     if (chunk_clips > B) chunk_clips = B;
     rc = ensure_slots(plan, n_streams, chunk_clips, n, T, 0);
     if (rc != HLMC_OK) return rc;
-    const int64_t dp = (n + 3) & ~int64_t(3);
+    // device row pitch: every row 16-byte aligned - or, for float32 rows of even length that need no pad, the
+    // host layout itself (rows 8-byte aligned, which the TMA staging handles), so that the H2D copy is one
+    // linear transfer instead of a pitched 2-D one
+    const bool linear = (sample_format == HLMC_SAMPLES_F32) && (n % 2 == 0) && (n_valid == n) && (h_pitch == n);
+    const int64_t dp = linear ? n : ((n + 3) & ~int64_t(3));
     const int64_t rp = (n_valid + 7) & ~int64_t(7);           // PCM16 staging pitch (16-B rows)
     const bool pcm = (sample_format == HLMC_SAMPLES_PCM16);
     const size_t esz = pcm ? 2 : 4;
@@ -1025,6 +1029,8 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
             CK(cudaMemcpy2DAsync(s.d_raw, (size_t)rp * 2, src, (size_t)h_pitch * 2, (size_t)n_valid * 2,
                                  (size_t)c, cudaMemcpyHostToDevice, s.stream));
             CK(launch_pcm16_to_f32(s.d_raw, rp, s.d_wave, dp, c, n_valid, n, s.stream));
+        } else if (linear) {
+            CK(cudaMemcpyAsync(s.d_wave, src, (size_t)c * n * 4, cudaMemcpyHostToDevice, s.stream));
         } else {
             CK(cudaMemcpy2DAsync(s.d_wave, (size_t)dp * 4, src, (size_t)h_pitch * 4, (size_t)n_valid * 4,
                                  (size_t)c, cudaMemcpyHostToDevice, s.stream));
