@@ -738,6 +738,8 @@ static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, 
     const bool fused = (d_pooled != nullptr && d_logmel == nullptr);
     if ((!fused && !d_logmel) || !d_clipmax) return fail(HLMC_ERR_PARAM, "d_logmel and d_clipmax are required");
     if (fused && !d_stats) return fail(HLMC_ERR_PARAM, "the pooled path needs a (B, 5, T) d_stats buffer");
+    if (fused && !db_pool_fits(plan->p.n_mels, pool_mfcc ? plan->ncp : 0, (int)T))
+        return fail(HLMC_ERR_UNSUPPORTED, "n_mels / n_mfcc too large for the fused pooling kernel: use hlmc_extract_device + hlmc_pool_device");
     if (fused && pool_chroma && !d_chroma) return fail(HLMC_ERR_PARAM, "pooled chroma columns need d_chroma");
     if ((d_mfcc || (fused && pool_mfcc)) && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
     CK(cudaSetDevice(plan->device));
@@ -1040,7 +1042,7 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
         }
         plan->last_h2d += c * n_valid * (int64_t)esz;
         // only pooled columns wanted: dB + DCT + pooling fused, no log-mel / MFCC arrays in HBM
-        const bool fused = io->pooled && !io->logmel && !io->mfcc;
+        const bool fused = io->pooled && !io->logmel && !io->mfcc && db_pool_fits(nm, want_mfcc ? plan->ncp : 0, (int)T);
         rc = extract_device_impl(plan, s.d_wave, c, n, dp, fused ? nullptr : s.d_logmel,
                                  (want_mfcc && !fused) ? s.d_mfcc : nullptr,
                                  s.d_stats, s.d_status, s.d_clipmax, want_chroma ? s.d_chroma : nullptr,

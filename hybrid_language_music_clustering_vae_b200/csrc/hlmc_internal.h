@@ -119,6 +119,7 @@ cudaError_t launch_tuning(const float2* cand, const int* cand_count, int T, int 
 cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, cudaStream_t stream);
 cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream);
 cudaError_t launch_db_pool(const DbArgs& a, const PoolArgs& pa, int num_sms, cudaStream_t stream);
+bool db_pool_fits(int n_mels, int ncp, int T);   // the fused kernel's tile fits shared memory
 cudaError_t launch_rowmax(const float* in, unsigned int* clipmax, long long B, long long per_clip,
                           cudaStream_t stream);
 cudaError_t launch_power_to_db(const float* in, float* out, const unsigned int* clipmax, long long B,

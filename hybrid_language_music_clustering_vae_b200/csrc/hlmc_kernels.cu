@@ -2018,12 +2018,19 @@ static cudaError_t launch_db_nc(const DbArgs& a, cudaStream_t stream) {
 // (T = 130 -> one tile of 160; T = 1292 -> six tiles of 224), between 128 and 256.
 constexpr int kPoolMinThreads = 128, kPoolMaxThreads = 256;
 constexpr int kPoolRowsPerThread = kMaxMelGroups * 32 / kPoolMinThreads;   // n_mels <= 256
-static int pool_threads(int T) {
+static int pool_smem_bytes(int n_mels, int nc, int nt) {
+    const int rows = (n_mels + 1) / 2;
+    return (((rows * nc + 3) & ~3) + nt * (n_mels + 1) + nt * (nc + 1)) * 4;
+}
+// 0 if even the smallest tile does not fit the 227 KB of shared memory (n_mels = 256 with 128 coefficients)
+static int pool_threads(int T, int n_mels, int nc) {
     const int tiles = (T + kPoolMaxThreads - 1) / kPoolMaxThreads;
     int nt = (((T + tiles - 1) / tiles) + 31) & ~31;
     if (nt < kPoolMinThreads) nt = kPoolMinThreads;
-    return nt;
+    while (nt > kPoolMinThreads && pool_smem_bytes(n_mels, nc, nt) > 224 * 1024) nt -= 32;
+    return pool_smem_bytes(n_mels, nc, nt) <= 224 * 1024 ? nt : 0;
 }
+bool db_pool_fits(int n_mels, int ncp, int T) { return pool_threads(T > 0 ? T : 1, n_mels, ncp) > 0; }
 
 template <int NC>
 __global__ void __launch_bounds__(kPoolMaxThreads) db_pool(const DbArgs a, const PoolArgs pa) {
@@ -2190,9 +2197,9 @@ __global__ void __launch_bounds__(kPoolMaxThreads) db_pool(const DbArgs a, const
 template <int NC>
 static cudaError_t launch_db_pool_nc(const DbArgs& a, const PoolArgs& pa, int num_sms, cudaStream_t stream) {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;
-    const int rows = (a.n_mels + 1) / 2;
-    const int nt = pool_threads(a.T);
-    const int smem = (((rows * NC + 3) & ~3) + nt * (a.n_mels + 1) + nt * (NC + 1)) * 4;
+    const int nt = pool_threads(a.T, a.n_mels, NC);
+    if (nt == 0) return cudaErrorInvalidConfiguration;
+    const int smem = pool_smem_bytes(a.n_mels, NC, nt);
     cudaError_t e = cudaFuncSetAttribute(db_pool<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int per_sm = (227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1;

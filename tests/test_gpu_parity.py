@@ -528,3 +528,18 @@ def test_fused_pooled_only_path(built, kw):
     z = ex.extract_pooled_device(torch.zeros((2, 22050), device="cuda"))["pooled"].cpu().numpy()
     nm = ex.n_mels
     assert np.all(z[:, nm:2 * nm] == 0.0)
+
+
+def test_fused_pooling_falls_back_when_the_tile_does_not_fit(built):
+    """n_mels = 256 with 128 coefficients exceeds the fused kernel's shared-memory tile: the device entry says so,
+    the host pipeline's pooled-only mode takes db_dct + pool_kernel instead."""
+    import torch
+
+    hl = built
+    ex = hl.FeatureExtractor(n_mels=256, n_mfcc=128, ref=np.max)
+    y = hl.synth.synth_batch(5, 22050, seed=3)
+    with pytest.raises(hl.UnsupportedError):
+        ex.extract_pooled_device(torch.from_numpy(y).cuda())
+    a = ex.extract_host(y, pooled=True)
+    b = ex.extract_host(y, logmel=False, mfcc=False, stats=False, pooled=True)
+    assert b["pooled"].shape == (5, 2 * 256 + 2 * 128 + 10) and np.array_equal(a["pooled"], b["pooled"])

@@ -55,3 +55,55 @@ def test_stft_matches_torch():
     Dt = torch.stft(torch.from_numpy(y).double(), 2048, 512, window=torch.hann_window(2048, dtype=torch.float64),
                     center=True, pad_mode="constant", return_complex=True).numpy()
     assert np.abs(D - Dt).max() <= 1e-5 * np.abs(Dt).max()
+
+
+def _music(seed, n=22050):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / SR
+    f0 = rng.uniform(110, 660)
+    y = sum((0.4 / k) * np.sin(2 * np.pi * f0 * k * t + rng.uniform(0, 6)) for k in range(1, 9)) * np.exp(-1.5 * t)
+    return (y + 0.01 * rng.standard_normal(n)).astype(np.float32)
+
+
+def test_melspectrogram_matches_torchaudio():
+    """torchaudio.transforms.MelSpectrogram with the slaney scale / norm is torchaudio's librosa-compatible
+    configuration (float32 STFT): an implementation written by others against the same definition."""
+    ta = pytest.importorskip("torchaudio")
+    torch = pytest.importorskip("torch")
+    tr = ta.transforms.MelSpectrogram(sample_rate=SR, n_fft=2048, hop_length=512, n_mels=128, power=2.0, center=True,
+                                      pad_mode="constant", norm="slaney", mel_scale="slaney")
+    for seed in (3, 4):
+        y = _music(seed)
+        want = tr(torch.from_numpy(y)).numpy()
+        got = orc.melspectrogram(y=y, sr=SR)
+        assert got.shape == want.shape == (128, 44)
+        assert np.abs(got - want).max() <= 2e-5 * want.max()
+        # the dB image the scripts store: well inside the 0.01 dB budget wherever it is not on the -80 dB floor
+        a, b = orc.power_to_db(got, ref=np.max), orc.power_to_db(want, ref=np.max)
+        assert np.abs(a - b)[b > -79.0].max() <= 5e-3
+
+
+def test_mfcc_matches_torchaudio():
+    """torchaudio.transforms.MFCC (log_mels=False) = DCT-II ortho of amplitude_to_DB(power mel, top_db=80): the
+    chain librosa.feature.mfcc runs, from an independent code base."""
+    ta = pytest.importorskip("torchaudio")
+    torch = pytest.importorskip("torch")
+    tr = ta.transforms.MFCC(sample_rate=SR, n_mfcc=40, dct_type=2, norm="ortho", log_mels=False,
+                            melkwargs=dict(n_fft=2048, hop_length=512, n_mels=128, power=2.0, center=True,
+                                           pad_mode="constant", norm="slaney", mel_scale="slaney"))
+    for seed in (5, 6):
+        y = _music(seed)
+        want = tr(torch.from_numpy(y)).numpy()
+        got = orc.mfcc(y=y, sr=SR, n_mfcc=40, n_fft=2048, hop_length=512)
+        assert got.shape == want.shape == (40, 44)
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_spectral_centroid_matches_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    torch = pytest.importorskip("torch")
+    y = _music(7)
+    want = ta.functional.spectral_centroid(torch.from_numpy(y), SR, pad=0, window=torch.hann_window(2048), n_fft=2048,
+                                           hop_length=512, win_length=2048).numpy()
+    got = orc.spectral_centroid(y=y, sr=SR, pad_mode="reflect")[0]      # torchaudio's spectrogram pads by reflection
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
