@@ -93,14 +93,14 @@ subprocess.run(f"cd {tmp} && rm -f *.cubin && cuobjdump -xelf all {lib} > /dev/n
                f"nvdisasm --print-line-info -c hlmc_kernels.sm_100a.cubin > k.dis 2>/dev/null", shell=True, check=True)
 frames = clips * 130
 res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_by_line.py"), src_csv, f"{tmp}/k.dis",
-                      "frames_fast_2048ILi16", str(frames), "80"], capture_output=True, text=True)
+                      "frames_fast_2048ILi16ELb0ELb1E", str(frames), "80"], capture_output=True, text=True)
 with open(os.path.join(out_dir, f"{tag}_frames_fast_by_line.txt"), "w") as f:
     f.write("# executed warp-instructions, share of stall samples and shared-memory wavefronts per frame,\n"
             "# by CUDA source line (ncu source page joined with nvdisasm line info)\n" + res.stdout + res.stderr[-2000:])
 # SASS listing of the frames kernel
 sass = subprocess.run(f"cuobjdump -sass {lib}", shell=True, capture_output=True, text=True).stdout
 chunks = sass.split("\tFunction : ")
-pick = [c for c in chunks if c.startswith("_ZN4hlmc16frames_fast_2048ILi16")] + [c for c in chunks if c.startswith("_ZN4hlmc6db_dctILi40")]
+pick = [c for c in chunks if c.startswith("_ZN4hlmc16frames_fast_2048ILi16ELb0ELb1E")] + [c for c in chunks if c.startswith("_ZN4hlmc6db_dctILi40")]
 with gzip.open(os.path.join(out_dir, f"{tag}_sass_frames_fast_db_dct.txt.gz"), "wt") as f:
     f.write("\n\tFunction : ".join(pick))
 mix = {}
@@ -121,7 +121,12 @@ ev = []
 for line in pick[0].splitlines() if pick else []:
     if any(op in line for op in ("UBLKCP", "SYNCS", "MUFU.SQRT", "FENCE.VIEW.ASYNC", "UTMA")):
         ev.append(line.rstrip())
+packed = {op: [l.rstrip() for l in (pick[0].splitlines() if pick else []) if f" {op} " in l] for op in ("FFMA2", "FADD2", "FMUL2")}
 with open(os.path.join(out_dir, f"{tag}_sass_evidence.txt"), "w") as f:
-    f.write("# frames_fast_2048<16,false>: TMA bulk copy (UBLKCP), mbarrier (SYNCS), async-proxy fence, MUFU lines\n")
+    f.write("# frames_fast_2048<16,*>: TMA bulk copy (UBLKCP), mbarrier (SYNCS), async-proxy fence, MUFU lines\n")
     f.write("\n".join(ev) + "\n")
+    f.write("# Blackwell packed FP32 (sm_100 only): " + ", ".join(f"{op} x{len(v)}" for op, v in packed.items()) +
+            " static instructions; first lines of each (operand swizzles .LO_HI / sign patterns .NP fold the +-i rotations):\n")
+    for op, v in packed.items():
+        f.write("\n".join(v[:4]) + "\n")
 print("wrote profiles/", tag)
