@@ -296,9 +296,25 @@ def main():
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the bound of this path: a bare pinned-host -> device copy of the same input (SURVEY 8d asks for it next
+        # to the result); measured on this rank with nothing else on the bus
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d_flat = d_store.view(-1)[: B * n].view(B, n)
+        d_flat.copy_(h_wave_t, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        c0.record()
+        for _ in range(3):
+            d_flat.copy_(h_wave_t, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        h2d_peak = 3 * h_wave_t.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        d_wave.copy_(h_wave_t, non_blocking=True)            # restore the pitched device copy
+        torch.cuda.synchronize(dev)
         e2e = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
                "pcie_gbs": (h2d + d2h) * args.steps / dt / 1e9,
+               "h2d_gbs": h2d * args.steps / dt / 1e9, "h2d_bare_copy_gbs": h2d_peak,
+               "bound": "PCIe host->device: the step's input alone takes h2d_bytes / h2d_bare_copy_gbs",
                "checksum": float(h_out["logmel"][0, 0, :4].sum())}
 
     # ---- secondary e2e: the same clips as 16-bit PCM (what the WAV files hold); the device does
