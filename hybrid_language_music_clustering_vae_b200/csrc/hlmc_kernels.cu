@@ -2008,42 +2008,51 @@ static cudaError_t launch_db_nc(const DbArgs& a, cudaStream_t stream) {
 // power_to_db + DCT-II + time pooling in one kernel: what 1_preprocessing.py keeps of a clip
 // is np.mean / np.std over frames of every log-mel band, MFCC and statistic ([R] src/1_preprocessing.py:
 // 115-124), so when the caller does not ask for the (B, n_mels, T) / (B, n_mfcc, T) arrays they are never
-// written to HBM.  One CTA per clip, frames in tiles of 128: phase 1 is db_dct's arithmetic (one thread per
-// frame) into a shared-memory tile, phase 2 turns the tile by 90 degrees (one thread per band / coefficient):
-// mean and squared deviations of the tile's frames in two passes over shared memory, tiles combined with
-// Chan's update (a constant row has exactly zero variance; no cancellation however far the mean is from 0).
+// written to HBM.  One CTA of 128 threads per clip, two phases over the clip's frame-major mel power:
+//   A. one thread per mel band walks the frames (every load a coalesced n_mels-float row), converts to dB and
+//      pools in chunks of 16 frames: chunk mean and squared deviations from registers, chunks merged with
+//      Chan's update (a constant row has exactly zero variance, no cancellation far from zero);
+//   B. one thread per frame runs db_dct's folded DCT (its second read of the row hits L1 / L2) into a small
+//      shared-memory tile of coefficients, which one thread per coefficient pools the same way.
 // The 5 statistics rows and the 24 chroma rows are pooled from HBM with pool_kernel's two-pass arithmetic.
+// 31 KB of shared memory per CTA: 7 CTAs per SM overlap each other's phases.
 // ---------------------------------------------------------------------------
-// Threads per CTA = frames per tile, chosen at launch so that the clip's T frames fill the tiles evenly
-// (T = 130 -> one tile of 160; T = 1292 -> six tiles of 224), between 128 and 256.
+// Threads per CTA = frames per phase-B round, chosen at launch so that the clip's T frames fill the rounds
+// evenly (T = 130 -> one round of 160; T = 1292 -> six rounds of 224), between 128 and 256.
 constexpr int kPoolMinThreads = 128, kPoolMaxThreads = 256;
 constexpr int kPoolRowsPerThread = kMaxMelGroups * 32 / kPoolMinThreads;   // n_mels <= 256
+constexpr int kPoolChunk = 16;
+
+static int pool_threads(int T) {
+    const int rounds = (T + kPoolMaxThreads - 1) / kPoolMaxThreads;
+    int nt = (((T + rounds - 1) / rounds) + 31) & ~31;
+    return nt < kPoolMinThreads ? kPoolMinThreads : nt;
+}
 static int pool_smem_bytes(int n_mels, int nc, int nt) {
     const int rows = (n_mels + 1) / 2;
-    return (((rows * nc + 3) & ~3) + nt * (n_mels + 1) + nt * (nc + 1)) * 4;
+    return (((rows * nc + 3) & ~3) + nt * (nc + 1)) * 4;
 }
-// 0 if even the smallest tile does not fit the 227 KB of shared memory (n_mels = 256 with 128 coefficients)
-static int pool_threads(int T, int n_mels, int nc) {
-    const int tiles = (T + kPoolMaxThreads - 1) / kPoolMaxThreads;
-    int nt = (((T + tiles - 1) / tiles) + 31) & ~31;
-    if (nt < kPoolMinThreads) nt = kPoolMinThreads;
-    while (nt > kPoolMinThreads && pool_smem_bytes(n_mels, nc, nt) > 224 * 1024) nt -= 32;
-    return pool_smem_bytes(n_mels, nc, nt) <= 224 * 1024 ? nt : 0;
+bool db_pool_fits(int n_mels, int ncp, int T) { return pool_smem_bytes(n_mels, ncp, pool_threads(T > 0 ? T : 1)) <= 224 * 1024; }
+
+// Chan's update of (mean, M2) over n_a samples with a chunk of n_b samples given by its (mean, M2)
+__device__ __forceinline__ void chan_merge(float& mean, float& m2, int na, float cmean, float cm2, int nb) {
+    if (na == 0) { mean = cmean; m2 = cm2; return; }
+    const float fa = float(na), fb = float(nb), delta = cmean - mean;
+    mean = fmaf(delta, fb / (fa + fb), mean);
+    m2 += cm2 + delta * delta * (fa * fb / (fa + fb));
 }
-bool db_pool_fits(int n_mels, int ncp, int T) { return pool_threads(T > 0 ? T : 1, n_mels, ncp) > 0; }
 
 template <int NC>
 __global__ void __launch_bounds__(kPoolMaxThreads) db_pool(const DbArgs a, const PoolArgs pa) {
     extern __shared__ __align__(16) float sP[];
     constexpr int H = NC / 2;
+    const int NT = blockDim.x;                      // = frames per phase-B round
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NT = blockDim.x;                      // = frames per tile
     const int half = a.n_mels >> 1;
     const int rows = (a.n_mels + 1) >> 1;
-    const int TS = a.n_mels + 1, MS = NC + 1;
+    constexpr int MS = NC + 1;
     float* sD = sP;
-    float* tile = sD + ((rows * NC + 3) & ~3);
-    float* tileM = tile + NT * TS;
+    float* tileM = sD + ((rows * NC + 3) & ~3);
     if constexpr (NC > 0) {
         for (int i = tid; i < rows * NC; i += NT) {
             const int n = i / NC, j = i - n * NC;
@@ -2061,119 +2070,121 @@ __global__ void __launch_bounds__(kPoolMaxThreads) db_pool(const DbArgs a, const
         const float ref_db = (a.ref_mode == 1) ? maxa : db10(fmaxf(a.amin, fabsf(a.ref_value)));
         const float floor_db = (a.top_db >= 0.0f) ? (maxa - ref_db) - a.top_db : -CUDART_INF_F;
         const float floor_m = db10(fmaxf(1e-10f, pmax)) - 80.0f;
-        float mean_m[kPoolRowsPerThread], m2_m[kPoolRowsPerThread];       // running mean / sum of squared deviations
-#pragma unroll
-        for (int r = 0; r < kPoolRowsPerThread; ++r) { mean_m[r] = 0.f; m2_m[r] = 0.f; }
-        float mean_c = 0.f, m2_c = 0.f;
-        // one tile's column: two passes over shared memory, then Chan's parallel update of (mean, M2)
-        auto absorb = [&](const float* col, int stride, int nt, int t0, float& mean, float& m2) {
-            float sum = 0.0f;
-            for (int f = 0; f < nt; ++f) sum += col[f * stride];
-            const float tmean = sum / float(nt);
-            float q = 0.0f;
-            for (int f = 0; f < nt; ++f) { const float d = col[f * stride] - tmean; q = fmaf(d, d, q); }
-            if (t0 == 0) { mean = tmean; m2 = q; }
-            else {
-                const float na = float(t0), nb = float(nt), delta = tmean - mean;
-                mean = fmaf(delta, nb / (na + nb), mean);
-                m2 += q + delta * delta * (na * nb / (na + nb));
-            }
-        };
-        for (int t0 = 0; t0 < a.T; t0 += NT) {
-            const int t = t0 + tid;
-            if (t < a.T) {
-                // ---- phase 1: this thread's frame: dB of every band into the tile, DCT in registers
-                const float* row = a.mel_in + ((size_t)b * a.T + t) * a.n_mels;
-                float* trow = tile + tid * TS;
-                float2 acc[NC > 0 ? H : 1];
-#pragma unroll
-                for (int c = 0; c < H; ++c) acc[c] = make_float2(0.f, 0.f);
-                auto to_db = [&](float p, int m) -> float {
-                    const float adb = db10(fmaxf(a.amin, p));
-                    trow[m] = fmaxf(adb - ref_db, floor_db);
-                    const float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
-                    return fmaxf(x, floor_m);
-                };
-                constexpr int MB = 4;
-                for (int n0 = 0; n0 < half; n0 += MB) {
-                    float lo[MB], hi[MB];
-                    if (vec) {
-                        const float4 u = __ldg(reinterpret_cast<const float4*>(row + n0));
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(row + a.n_mels - MB - n0));
-                        lo[0] = u.x; lo[1] = u.y; lo[2] = u.z; lo[3] = u.w;
-                        hi[0] = v.w; hi[1] = v.z; hi[2] = v.y; hi[3] = v.x;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < MB; ++j) {
-                            const bool in = n0 + j < half;
-                            lo[j] = in ? row[n0 + j] : 0.0f;
-                            hi[j] = in ? row[a.n_mels - 1 - n0 - j] : 0.0f;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < MB; ++j) {
-                        const int n = n0 + j;
-                        if (n >= half) break;
-                        const float xl = to_db(lo[j], n), xh = to_db(hi[j], a.n_mels - 1 - n);
-                        if constexpr (NC > 0) {
-                            const float2 sf = make_float2(xl + xh, xl + xh), df = make_float2(xl - xh, xl - xh);
-                            const float4* d4 = reinterpret_cast<const float4*>(sD + n * NC);
-#pragma unroll
-                            for (int c = 0; c < H / 4; ++c) {
-                                const float4 e = d4[c], o = d4[H / 4 + c];
-                                acc[2 * c] = __ffma2_rn(make_float2(e.x, e.y), sf, acc[2 * c]);
-                                acc[2 * c + 1] = __ffma2_rn(make_float2(e.z, e.w), sf, acc[2 * c + 1]);
-                                acc[H / 2 + 2 * c] = __ffma2_rn(make_float2(o.x, o.y), df, acc[H / 2 + 2 * c]);
-                                acc[H / 2 + 2 * c + 1] = __ffma2_rn(make_float2(o.z, o.w), df, acc[H / 2 + 2 * c + 1]);
-                            }
-                        }
-                    }
-                }
-                if (a.n_mels & 1) {
-                    const float x = to_db(row[half], half);
-                    if constexpr (NC > 0) {
-#pragma unroll
-                        for (int c = 0; c < H / 2; ++c)
-                            acc[c] = __ffma2_rn(make_float2(sD[half * NC + 2 * c], sD[half * NC + 2 * c + 1]),
-                                                make_float2(x, x), acc[c]);
-                    }
-                }
-                if constexpr (NC > 0) {
-                    float* mrow = tileM + tid * MS;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        mrow[2 * j] = (j & 1) ? acc[j >> 1].y : acc[j >> 1].x;
-                        mrow[2 * j + 1] = (j & 1) ? acc[H / 2 + (j >> 1)].y : acc[H / 2 + (j >> 1)].x;
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- phase 2: one thread per band / coefficient walks the tile's frames
-            const int nt = (a.T - t0 < NT) ? a.T - t0 : NT;
-#pragma unroll
-            for (int r = 0; r < kPoolRowsPerThread; ++r) {
-                const int m = tid + r * NT;
-                if (m < a.n_mels) absorb(tile + m, TS, nt, t0, mean_m[r], m2_m[r]);
-            }
-            if (NC > 0 && pa.with_mfcc && tid < a.n_mfcc) absorb(tileM + tid, MS, nt, t0, mean_c, m2_c);
-            __syncthreads();
-        }
-        // ---- the clip's pooled row: [mel mean | mel std | mfcc mean | mfcc std | 5 x (mean, std) | chroma mean | chroma std]
+        const float* clip_mel = a.mel_in + (size_t)b * a.T * a.n_mels;
         float* out = pa.pooled + (size_t)b * pa.pooled_w;
-        const int nc_out = pa.with_mfcc ? a.n_mfcc : 0;
+
+        // ---- phase A: log-mel bands.  Thread m reads element m of every frame's row.
 #pragma unroll
         for (int r = 0; r < kPoolRowsPerThread; ++r) {
             const int m = tid + r * NT;
-            if (m < a.n_mels) {
-                out[m] = mean_m[r];
-                out[a.n_mels + m] = sqrtf(m2_m[r] * invT);
+            if (m >= a.n_mels) continue;
+            float mean = 0.0f, m2 = 0.0f;
+            for (int f0 = 0; f0 < a.T; f0 += kPoolChunk) {
+                const int nb = (a.T - f0 < kPoolChunk) ? a.T - f0 : kPoolChunk;
+                float x[kPoolChunk];
+#pragma unroll
+                for (int u = 0; u < kPoolChunk; ++u)          // independent loads first
+                    x[u] = (u < nb) ? __ldg(clip_mel + (size_t)(f0 + u) * a.n_mels + m) : 0.0f;
+                float sum = 0.0f;
+#pragma unroll
+                for (int u = 0; u < kPoolChunk; ++u) {
+                    x[u] = fmaxf(db10(fmaxf(a.amin, x[u])) - ref_db, floor_db);
+                    sum += (u < nb) ? x[u] : 0.0f;
+                }
+                const float cmean = sum / float(nb);
+                float q = 0.0f;
+#pragma unroll
+                for (int u = 0; u < kPoolChunk; ++u) { const float d = (u < nb) ? x[u] - cmean : 0.0f; q = fmaf(d, d, q); }
+                chan_merge(mean, m2, f0, cmean, q, nb);
+            }
+            out[m] = mean;
+            out[a.n_mels + m] = sqrtf(m2 * invT);
+        }
+
+        // ---- phase B: MFCC.  One thread per frame, tiles of NT frames, then one thread per coefficient.
+        if constexpr (NC > 0) {
+            if (pa.with_mfcc) {
+                float mean_c = 0.0f, m2_c = 0.0f;
+                for (int t0 = 0; t0 < a.T; t0 += NT) {
+                    const int t = t0 + tid;
+                    if (t < a.T) {
+                        const float* row = clip_mel + (size_t)t * a.n_mels;
+                        float2 acc[H];
+#pragma unroll
+                        for (int c = 0; c < H; ++c) acc[c] = make_float2(0.f, 0.f);
+                        auto mdb = [&](float p) -> float {      // librosa.feature.mfcc: power_to_db(S), ref = 1, top_db = 80
+                            const float x = same_amin ? db10(fmaxf(a.amin, p)) : db10(fmaxf(1e-10f, p));
+                            return fmaxf(x, floor_m);
+                        };
+                        constexpr int MB = 4;
+                        for (int n0 = 0; n0 < half; n0 += MB) {
+                            float lo[MB], hi[MB];
+                            if (vec) {
+                                const float4 u = __ldg(reinterpret_cast<const float4*>(row + n0));
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(row + a.n_mels - MB - n0));
+                                lo[0] = u.x; lo[1] = u.y; lo[2] = u.z; lo[3] = u.w;
+                                hi[0] = v.w; hi[1] = v.z; hi[2] = v.y; hi[3] = v.x;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < MB; ++j) {
+                                    const bool in = n0 + j < half;
+                                    lo[j] = in ? row[n0 + j] : 0.0f;
+                                    hi[j] = in ? row[a.n_mels - 1 - n0 - j] : 0.0f;
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < MB; ++j) {
+                                const int n = n0 + j;
+                                if (n >= half) break;
+                                const float xl = mdb(lo[j]), xh = mdb(hi[j]);
+                                const float2 sf = make_float2(xl + xh, xl + xh), df = make_float2(xl - xh, xl - xh);
+                                const float4* d4 = reinterpret_cast<const float4*>(sD + n * NC);
+#pragma unroll
+                                for (int c = 0; c < H / 4; ++c) {
+                                    const float4 e = d4[c], o = d4[H / 4 + c];
+                                    acc[2 * c] = __ffma2_rn(make_float2(e.x, e.y), sf, acc[2 * c]);
+                                    acc[2 * c + 1] = __ffma2_rn(make_float2(e.z, e.w), sf, acc[2 * c + 1]);
+                                    acc[H / 2 + 2 * c] = __ffma2_rn(make_float2(o.x, o.y), df, acc[H / 2 + 2 * c]);
+                                    acc[H / 2 + 2 * c + 1] = __ffma2_rn(make_float2(o.z, o.w), df, acc[H / 2 + 2 * c + 1]);
+                                }
+                            }
+                        }
+                        if (a.n_mels & 1) {
+                            const float x = mdb(row[half]);
+#pragma unroll
+                            for (int c = 0; c < H / 2; ++c)
+                                acc[c] = __ffma2_rn(make_float2(sD[half * NC + 2 * c], sD[half * NC + 2 * c + 1]),
+                                                    make_float2(x, x), acc[c]);
+                        }
+                        float* mrow = tileM + tid * MS;
+#pragma unroll
+                        for (int j = 0; j < H; ++j) {
+                            mrow[2 * j] = (j & 1) ? acc[j >> 1].y : acc[j >> 1].x;
+                            mrow[2 * j + 1] = (j & 1) ? acc[H / 2 + (j >> 1)].y : acc[H / 2 + (j >> 1)].x;
+                        }
+                    }
+                    __syncthreads();
+                    const int nt = (a.T - t0 < NT) ? a.T - t0 : NT;
+                    if (tid < a.n_mfcc) {
+                        const float* col = tileM + tid;
+                        float sum = 0.0f;
+                        for (int f = 0; f < nt; ++f) sum += col[f * MS];
+                        const float cmean = sum / float(nt);
+                        float q = 0.0f;
+                        for (int f = 0; f < nt; ++f) { const float d = col[f * MS] - cmean; q = fmaf(d, d, q); }
+                        chan_merge(mean_c, m2_c, t0, cmean, q, nt);
+                    }
+                    __syncthreads();
+                }
+                if (tid < a.n_mfcc) {
+                    out[2 * a.n_mels + tid] = mean_c;
+                    out[2 * a.n_mels + a.n_mfcc + tid] = sqrtf(m2_c * invT);
+                }
             }
         }
-        if (NC > 0 && pa.with_mfcc && tid < a.n_mfcc) {
-            out[2 * a.n_mels + tid] = mean_c;
-            out[2 * a.n_mels + a.n_mfcc + tid] = sqrtf(m2_c * invT);
-        }
-        const int base = 2 * a.n_mels + 2 * nc_out;
+
+        // ---- statistics and chroma rows: warp per row, two passes over HBM (pool_kernel's arithmetic)
+        const int base = 2 * a.n_mels + 2 * ((NC > 0 && pa.with_mfcc) ? a.n_mfcc : 0);
         for (int r = warp; r < 5 + pa.n_chroma; r += NT / 32) {
             const float* src = (r < 5) ? pa.stats + ((size_t)b * 5 + r) * a.T
                                        : pa.chroma + ((size_t)b * pa.n_chroma + (r - 5)) * a.T;
@@ -2197,12 +2208,14 @@ __global__ void __launch_bounds__(kPoolMaxThreads) db_pool(const DbArgs a, const
 template <int NC>
 static cudaError_t launch_db_pool_nc(const DbArgs& a, const PoolArgs& pa, int num_sms, cudaStream_t stream) {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;
-    const int nt = pool_threads(a.T, a.n_mels, NC);
-    if (nt == 0) return cudaErrorInvalidConfiguration;
+    const int nt = pool_threads(a.T);
     const int smem = pool_smem_bytes(a.n_mels, NC, nt);
+    if (smem > 224 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(db_pool<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    const int per_sm = (227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1;
+    int per_sm = (224 * 1024) / (smem + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
     long long grid = (long long)num_sms * per_sm;
     if (grid > a.B) grid = a.B;
     db_pool<NC><<<(unsigned)grid, nt, smem, stream>>>(a, pa);
