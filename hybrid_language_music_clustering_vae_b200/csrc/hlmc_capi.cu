@@ -678,11 +678,11 @@ static FrameArgs make_frame_args(const hlmc_plan* pl, const float* d_wave, int64
 static int run_frames(hlmc_plan* pl, const float* d_wave, int64_t B, int64_t n, int64_t pitch, int T,
                       float* d_mel, float* d_stats, int32_t* d_status, float* d_clipmax, float* d_spec,
                       cudaStream_t st, float2* cand = nullptr, int* cand_count = nullptr, int cand_cap = 0,
-                      int mel_frame_major = 0) {
+                      int mel_frame_major = 0, float* pstash = nullptr) {
     FrameArgs a = make_frame_args(pl, d_wave, B, n, pitch, T);
     a.mel_out = d_mel; a.stats = d_stats; a.status = d_status; a.mel_frame_major = mel_frame_major;
     a.clipmax = reinterpret_cast<unsigned int*>(d_clipmax); a.spec = d_spec;
-    a.cand = cand; a.cand_count = cand_count; a.cand_cap = cand_cap;
+    a.cand = cand; a.cand_count = cand_count; a.cand_cap = cand_cap; a.pstash = pstash;
     if (d_clipmax) CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));
     if (d_status) CK(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
     if (pl->fast_ok && !pl->force_generic && d_spec == nullptr) {
@@ -714,14 +714,21 @@ static int check_batch(const hlmc_plan* pl, const void* wave, int64_t B, int64_t
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// candidates + counts + tuning indices: what the tuning estimate needs
+static size_t chroma_ws_core(const hlmc_plan* plan, int64_t B, int64_t T) {
+    return align256((size_t)B * T * 4) + align256((size_t)B * 4) +
+           align256((size_t)B * T * plan->cand_per_frame * sizeof(float2));
+}
+
+// ... plus the power-spectrum stash (B, T, kStashFloats) that lets the projection skip a second STFT pass.  A
+// caller that passes only the core size still gets chroma, through the recomputing kernel.
 int64_t hlmc_chroma_workspace_bytes(hlmc_plan* plan, int64_t B, int64_t n) {
     if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
     int rc = ensure_chroma_tables(plan);
     if (rc != HLMC_OK) return rc;
     const int64_t T = hlmc_num_frames(&plan->p, n);
     if (T < 0) return T;
-    return (int64_t)(align256((size_t)B * T * 4) + align256((size_t)B * 4) +
-                     (size_t)B * T * plan->cand_per_frame * sizeof(float2));
+    return (int64_t)(chroma_ws_core(plan, B, T) + (size_t)B * T * kStashFloats * 4);
 }
 
 // d_pooled with d_logmel == NULL selects the fused path: dB, DCT and time pooling in one kernel, the
@@ -746,17 +753,20 @@ static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // chroma: piptrack candidates come out of the same pass as the other features
     float2* cand = nullptr; int* cand_count = nullptr; int* tuning_idx = nullptr; int cand_cap = 0;
+    float* pstash = nullptr;
     if (d_chroma) {
         rc = ensure_chroma_tables(plan);
         if (rc != HLMC_OK) return rc;
         if (plan->force_generic) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs the register-FFT kernel");
-        const int64_t need = hlmc_chroma_workspace_bytes(plan, B, n);
-        if (!d_work || work_bytes < need) return fail(HLMC_ERR_PARAM, "chroma workspace too small");
+        const size_t core = chroma_ws_core(plan, B, T);
+        if (!d_work || work_bytes < (int64_t)core) return fail(HLMC_ERR_PARAM, "chroma workspace too small");
         char* wsp = static_cast<char*>(d_work);
         cand_count = reinterpret_cast<int*>(wsp);                                   // (B, T), every entry written
         tuning_idx = reinterpret_cast<int*>(wsp + align256((size_t)B * T * 4));
         cand = reinterpret_cast<float2*>(wsp + align256((size_t)B * T * 4) + align256((size_t)B * 4));
         cand_cap = plan->cand_per_frame;
+        if (work_bytes >= (int64_t)(core + (size_t)B * T * kStashFloats * 4))
+            pstash = reinterpret_cast<float*>(wsp + core);
     }
     cudaEvent_t ev3[3] = {nullptr, nullptr, nullptr};
     if (plan->timing) {
@@ -772,7 +782,7 @@ static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, 
         own_scr = true;
     }
     rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_melscr, d_stats, d_status, d_clipmax, nullptr, st,
-                    cand, cand_count, cand_cap, 1);
+                    cand, cand_count, cand_cap, 1, pstash);
     if (rc != HLMC_OK) return rc;
     if (plan->timing) CK(cudaEventRecord(ev3[1], st));
     DbArgs d{};
@@ -782,9 +792,13 @@ static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, 
     d.amin = plan->p.amin; d.top_db = plan->p.top_db;
     auto run_chroma = [&]() -> int {
         CK(launch_tuning(cand, cand_count, (int)T, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
-        FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
         ChromaArgs ca{tuning_idx, plan->d_chroma_fb, d_chroma};
-        CK(launch_chroma_fast(a, ca, plan->d_fast, plan->ft, plan->num_sms, st));
+        if (pstash) {
+            CK(launch_chroma_project(pstash, ca, B, (int)T, plan->num_sms, st));
+        } else {                               // small workspace: second STFT pass
+            FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
+            CK(launch_chroma_fast(a, ca, plan->d_fast, plan->ft, plan->num_sms, st));
+        }
         return HLMC_OK;
     };
     if (fused) {

@@ -61,7 +61,11 @@ struct FrameArgs {
     int cand_cap;           // slots per frame
     int pip_klo, pip_khi;   // bins with fmin <= f < fmax
     float pip_threshold;    // 0.1
+    // power-spectrum stash for the chroma projection (register-FFT kernel with piptrack only) or NULL:
+    // (B, T, kStashFloats), each lane's 32 bins in its register order [lane][32], then bin 512
+    float* pstash;
 };
+constexpr int kStashFloats = 32 * 32 + 4;
 
 struct ChromaArgs {
     const int* tuning_idx;  // (B) index into the 100 pre-built filterbanks
@@ -114,6 +118,8 @@ cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const F
 int sub_smem_bytes(const FastTables& ft, int nwarps, int L);
 cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,
                                const FastTables& ft, int num_sms, cudaStream_t stream);
+cudaError_t launch_chroma_project(const float* pstash, const ChromaArgs& c, long long B, int T, int num_sms,
+                                  cudaStream_t stream);
 cudaError_t launch_tuning(const float2* cand, const int* cand_count, int T, int cand_per_frame, long long B,
                           const double* d_edges, float* tuning, int* tuning_idx, cudaStream_t stream);
 cudaError_t launch_frames_generic(const FrameArgs& a, const GenericTables& gt, cudaStream_t stream);

@@ -466,6 +466,19 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         int zc;
         frame_spectrum<PREF>(a, w, clip, t, nclip, nt, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
 
+        // ---- chroma_stft: keep the power spectrum for the projection that follows the tuning estimate
+        //      (8 coalesced 16-byte stores per lane, in the lane's register order: no second STFT pass)
+        if (PIP && a.pstash != nullptr) {
+            float* fr = a.pstash + ((size_t)b * a.T + t) * kStashFloats;
+            float4* dst = reinterpret_cast<float4*>(fr) + lane * 8;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                dst[q4] = make_float4(P[4 * q4].x, P[4 * q4 + 1].x, P[4 * q4 + 2].x, P[4 * q4 + 3].x);
+                dst[4 + q4] = make_float4(P[4 * q4].y, P[4 * q4 + 1].y, P[4 * q4 + 2].y, P[4 * q4 + 3].y);
+            }
+            if (lane == 31) fr[32 * 32] = p512;
+        }
+
         // ---- centroid / bandwidth (librosa.feature.spectral_centroid / _bandwidth)
         const float kcl = 16.0f * lane + 7.5f;
         const float kch = 1024.0f - 16.0f * lane - 7.5f;
@@ -1668,6 +1681,83 @@ chroma_fast_2048(const FrameArgs a, const ChromaArgs ca, const float* __restrict
         }
         __syncthreads();                       // the filterbank is replaced for the next clip
     }
+}
+
+// chroma projection from the stashed power spectrum (the default chroma path): one CTA per clip keeps the
+// clip's filterbank in shared memory; a warp takes two frames at a time so that every 16-byte filterbank
+// read feeds four FFMA2 (the filterbank read, 49 KB per frame, is what bounds this kernel).
+constexpr int kProjWarps = 8;
+__global__ void __launch_bounds__(kProjWarps * 32, 2)
+chroma_project(const float* __restrict__ pstash, const ChromaArgs ca, long long B, int T) {
+    extern __shared__ __align__(16) float fbs[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* src = ca.fb_all + (size_t)ca.tuning_idx[b] * kChromaFbFloats;
+        for (int i = tid; i < kChromaFbFloats / 4; i += kProjWarps * 32)
+            reinterpret_cast<float4*>(fbs)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        __syncthreads();
+        for (int t0 = 2 * warp; t0 < T; t0 += 2 * kProjWarps) {
+            const bool two = (t0 + 1) < T;
+            const float* fa = pstash + ((size_t)b * T + t0) * kStashFloats;
+            const float* fb = two ? fa + kStashFloats : fa;
+            float4 pa[8], pb[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                pa[q] = __ldg(reinterpret_cast<const float4*>(fa) + lane * 8 + q);
+                pb[q] = __ldg(reinterpret_cast<const float4*>(fb) + lane * 8 + q);
+            }
+            const float pa512 = __ldg(fa + 32 * 32), pb512 = __ldg(fb + 32 * 32);
+            float rawa[kChroma], rawb[kChroma];
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) {
+                const float4* fp = reinterpret_cast<const float4*>(fbs) + (c * 8) * 32 + lane;
+                float2 aa = make_float2(0.f, 0.f), ab = aa;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 f = fp[j4 * 32];
+                    aa = __ffma2_rn(make_float2(f.x, f.y), make_float2(pa[j4].x, pa[j4].y), aa);
+                    aa = __ffma2_rn(make_float2(f.z, f.w), make_float2(pa[j4].z, pa[j4].w), aa);
+                    ab = __ffma2_rn(make_float2(f.x, f.y), make_float2(pb[j4].x, pb[j4].y), ab);
+                    ab = __ffma2_rn(make_float2(f.z, f.w), make_float2(pb[j4].z, pb[j4].w), ab);
+                }
+                float ra = aa.x + aa.y, rb = ab.x + ab.y;
+                if (lane == 31) {
+                    const float wm = fbs[kChroma * 32 * 32 + c];
+                    ra = fmaf(wm, pa512, ra);
+                    rb = fmaf(wm, pb512, rb);
+                }
+                rawa[c] = warp_sum(ra);
+                rawb[c] = warp_sum(rb);
+            }
+            float mxa = 0.0f, mxb = 0.0f;
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) { mxa = fmaxf(mxa, fabsf(rawa[c])); mxb = fmaxf(mxb, fabsf(rawb[c])); }
+            const float inva = (mxa < 1.17549435e-38f) ? 1.0f : 1.0f / mxa;   // util.normalize(norm=inf)
+            const float invb = (mxb < 1.17549435e-38f) ? 1.0f : 1.0f / mxb;
+            float minea = rawa[0], mineb = rawb[0];
+#pragma unroll
+            for (int c = 1; c < kChroma; ++c) { minea = (lane == c) ? rawa[c] : minea; mineb = (lane == c) ? rawb[c] : mineb; }
+            if (lane < kChroma) {
+                float* o = ca.chroma + ((size_t)b * kChroma + lane) * T + t0;
+                o[0] = minea * inva;
+                if (two) o[1] = mineb * invb;
+            }
+        }
+        __syncthreads();                       // the filterbank is replaced for the next clip
+    }
+}
+
+cudaError_t launch_chroma_project(const float* pstash, const ChromaArgs& c, long long B, int T, int num_sms,
+                                  cudaStream_t stream) {
+    const int smem = kChromaFbFloats * 4;
+    cudaError_t e = cudaFuncSetAttribute(chroma_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    if (B <= 0 || T <= 0) return cudaSuccess;
+    long long grid = 2LL * num_sms;
+    if (grid > B) grid = B;
+    chroma_project<<<(unsigned)grid, kProjWarps * 32, smem, stream>>>(pstash, c, B, T);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,

@@ -393,6 +393,24 @@ def test_chroma_stft_and_tuning_on_device(built):
         # pooled chroma columns = mean / std over frames
         po = out["pooled"].cpu().numpy()
         assert np.abs(po[:, 346:358] - ch.mean(-1)).max() <= 1e-5 and np.abs(po[:, 358:370] - ch.std(-1)).max() <= 1e-5
+    # a workspace without room for the power-spectrum stash takes the recomputing kernel: same chroma
+    import ctypes as C
+    from hybrid_language_music_clustering_vae_b200._lib import lib
+    yd = torch.from_numpy(y).cuda()
+    B, T = len(y), 1 + n // 512
+    big = int(lib.hlmc_chroma_workspace_bytes(ex._plan, B, n))
+    small = big - B * T * (32 * 32 + 4) * 4
+    bufs = {k: torch.empty(sh, dtype=dt, device="cuda") for k, sh, dt in (
+        ("lm", (B, 128, T), torch.float32), ("mf", (B, 40, T), torch.float32), ("st", (B, 5, T), torch.float32),
+        ("sta", (B,), torch.int32), ("cm", (B,), torch.float32), ("ch", (B, 12, T), torch.float32),
+        ("tu", (B,), torch.float32), ("wk", (small,), torch.uint8))}
+    pt = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.hlmc_extract_device_ex(ex._plan, pt(yd), B, n, n, pt(bufs["lm"]), pt(bufs["mf"]), pt(bufs["st"]),
+                                    pt(bufs["sta"]), pt(bufs["cm"]), pt(bufs["ch"]), pt(bufs["tu"]), pt(bufs["wk"]),
+                                    small, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc == 0 and np.array_equal(bufs["tu"].cpu().numpy(), tu)
+    assert np.abs(bufs["ch"].cpu().numpy() - ch).max() <= 2e-6
     # the host pipeline produces the same chroma (chunked, overlapped copies)
     hp = ex.extract_host(y, chroma=True, pooled=True, chunk_clips=7)
     assert np.array_equal(hp["chroma"], ch) and np.array_equal(hp["tuning"], tu) and np.array_equal(hp["pooled"], po)
