@@ -36,7 +36,13 @@ for gen in (True, False):
 run(4, 30000, n_fft=1024, hop_length=256)
 run(4, 30000, n_fft=512, hop_length=128)
 run(4, 30000, n_fft=4096, hop_length=1024)
+run(6, 66150, n_fft=4096, hop_length=1024, pad_mode="reflect")
+run(4, 30000, n_fft=4096, hop_length=1024, generic=True)
 run(2, 661500)
+run(40, 66150)                      # the mixture DESIGN.md quotes
+run(8, 66150, window="hamming")     # window table path (no synthesised Hann, no early copy)
+run(8, 66150, n_mels=40)
+run(8, 66150, power=1.0)
 # throughput quick look
 ex = hl.FeatureExtractor(n_mfcc=40, ref=np.max)
 y = torch.randn(2000, 66152, device="cuda")[:, :66150] * 0.1
