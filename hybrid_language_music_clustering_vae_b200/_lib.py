@@ -22,7 +22,7 @@ EXPORTS = (
     "hlmc_plan_set_timing", "hlmc_plan_read_timing", "hlmc_extract_host_ex",
     "hlmc_chroma_workspace_bytes", "hlmc_extract_device_ex", "hlmc_pool_device_ex",
     "hlmc_extract_host_io", "hlmc_column_stats_device", "hlmc_standardize_device",
-    "hlmc_extract_pooled_device",
+    "hlmc_extract_pooled_device", "hlmc_graph_create", "hlmc_graph_launch", "hlmc_graph_destroy",
 )
 
 HLMC_OK, HLMC_ERR_PARAM, HLMC_ERR_UNSUPPORTED, HLMC_ERR_CUDA, HLMC_ERR_NOMEM = 0, -1, -2, -3, -4
@@ -90,6 +90,10 @@ def _load():
     lib.hlmc_chroma_workspace_bytes.argtypes = [vp, i64, i64]
     lib.hlmc_chroma_workspace_bytes.restype = i64
     lib.hlmc_extract_device_ex.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.hlmc_graph_create.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    lib.hlmc_graph_launch.argtypes = [vp, vp]
+    lib.hlmc_graph_destroy.argtypes = [vp]
+    lib.hlmc_graph_destroy.restype = None
     lib.hlmc_extract_pooled_device.argtypes = [vp, vp, i64, i64, i64, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.hlmc_pool_device_ex.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp]
     lib.hlmc_extract_host_io.argtypes = [vp, C.POINTER(HlmcHostIo)]

@@ -69,6 +69,31 @@ def _row_pitch(w):
     return w.shape[1] if w.shape[0] <= 1 else w.stride(0)
 
 
+class DeviceGraph:
+    """A captured ``extract_device`` call (``FeatureExtractor.capture_device``)."""
+
+    def __init__(self, extractor, handle, waves, out):
+        self._ex, self._h, self.waves, self.out = extractor, handle, waves, out
+
+    def replay(self, stream=None):
+        import torch
+
+        s = stream if stream is not None else torch.cuda.current_stream(self.waves.device)
+        _check(lib.hlmc_graph_launch(self._h, C.c_void_p(s.cuda_stream)))
+        return self.out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.hlmc_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FeatureExtractor:
     """Fused log-mel + MFCC + spectral statistics for batches of equal-length clips."""
 
@@ -244,6 +269,25 @@ class FeatureExtractor:
             _check(lib.hlmc_pool_device_ex(self._plan, ptr(logmel), ptr(mf), ptr(st), ptr(ch), B, T, ptr(po),
                                            C.c_void_p(stream)))
         return out
+
+    def capture_device(self, waves, *, mfcc=True, stats=True, status=True):
+        """Capture ``extract_device`` on this batch as a CUDA graph (small batches are launch-bound).
+
+        Returns a :class:`DeviceGraph`: write new audio into ``graph.waves`` (same shape), call
+        ``graph.replay()`` and read ``graph.out`` - the buffers the graph was captured with."""
+        import torch
+
+        waves = self._as_cuda_batch(waves)
+        if waves.shape[0] == 0:
+            raise ParameterError("cannot capture an empty batch")
+        out = self.extract_device(waves, mfcc=mfcc, stats=stats, status=status)
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        handle = C.c_void_p()
+        B, n = waves.shape
+        _check(lib.hlmc_graph_create(self._plan, ptr(waves), B, n, _row_pitch(waves), ptr(out["logmel"]),
+                                     ptr(out.get("mfcc")), ptr(out.get("stats")), ptr(out.get("status")),
+                                     ptr(out["clipmax"]), C.byref(handle)))
+        return DeviceGraph(self, handle, waves, out)
 
     def extract_pooled_device(self, waves, *, mfcc=True, chroma=False):
         """Only the time-pooled columns of a device-resident batch ([R] extract_all_features /

@@ -845,6 +845,67 @@ int hlmc_extract_pooled_device(hlmc_plan* plan, const float* d_wave, int64_t B, 
                                stream, nullptr, d_pooled, with_mfcc, with_chroma);
 }
 
+struct hlmc_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    float* d_melscr = nullptr;
+    int device = 0;
+};
+
+void hlmc_graph_destroy(hlmc_graph* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    cudaFree(g->d_melscr);
+    delete g;
+}
+
+int hlmc_graph_create(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                      float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status, float* d_clipmax,
+                      hlmc_graph** out) {
+    if (!out) return fail(HLMC_ERR_PARAM, "null argument");
+    *out = nullptr;
+    int64_t T;
+    int rc = check_batch(plan, d_wave, B, n, pitch, &T);
+    if (rc != HLMC_OK) return rc;
+    if (B == 0) return fail(HLMC_ERR_PARAM, "empty batch");
+    if (plan->timing) return fail(HLMC_ERR_PARAM, "switch per-kernel timing off before capturing a graph");
+    CK(cudaSetDevice(plan->device));
+    hlmc_graph* g = new hlmc_graph();
+    g->device = plan->device;
+    cudaStream_t cs = nullptr;
+    cudaError_t e = cudaMalloc((void**)&g->d_melscr, (size_t)B * T * plan->p.n_mels * 4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { hlmc_graph_destroy(g); return cuda_fail(e, "graph setup"); }
+    // one eager run first: function attributes and lazily built tables must exist before the capture
+    rc = extract_device_impl(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax, nullptr,
+                             nullptr, nullptr, 0, cs, g->d_melscr);
+    if (rc == HLMC_OK && (e = cudaStreamSynchronize(cs)) != cudaSuccess) rc = cuda_fail(e, "graph warm-up");
+    if (rc == HLMC_OK) {
+        e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamBeginCapture");
+        else {
+            rc = extract_device_impl(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax,
+                                     nullptr, nullptr, nullptr, 0, cs, g->d_melscr);
+            e = cudaStreamEndCapture(cs, &g->graph);
+            if (rc == HLMC_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamEndCapture");
+        }
+    }
+    if (rc == HLMC_OK && (e = cudaGraphInstantiate(&g->exec, g->graph, 0)) != cudaSuccess)
+        rc = cuda_fail(e, "cudaGraphInstantiate");
+    cudaStreamDestroy(cs);
+    if (rc != HLMC_OK) { hlmc_graph_destroy(g); return rc; }
+    *out = g;
+    return HLMC_OK;
+}
+
+int hlmc_graph_launch(hlmc_graph* g, void* stream) {
+    if (!g || !g->exec) return fail(HLMC_ERR_PARAM, "null graph");
+    CK(cudaGraphLaunch(g->exec, static_cast<cudaStream_t>(stream)));
+    return HLMC_OK;
+}
+
 int hlmc_plan_set_timing(hlmc_plan* plan, int enable) {
     if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
     plan->timing = enable ? 1 : 0;

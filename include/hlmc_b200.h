@@ -136,6 +136,18 @@ int hlmc_extract_device(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t
                         int64_t pitch, float *d_logmel, float *d_mfcc, float *d_stats,
                         int32_t *d_status, float *d_clipmax, void *stream);
 
+/* hlmc_extract_device captured once as a CUDA graph and replayed: for small batches (1-64 clips) the call is
+ * launch-bound (two memsets, a scratch allocation, two kernels), and a replay costs one graph launch.  The
+ * graph is bound to the buffers, shapes and plan it was captured with; the mel-power scratch belongs to it.
+ * The caller's per-file loop ([R] src/1_preprocessing.py:232-251) becomes: copy the next clip(s) into d_wave,
+ * hlmc_graph_launch, read the outputs.  */
+typedef struct hlmc_graph hlmc_graph;
+int hlmc_graph_create(hlmc_plan *plan, const float *d_wave, int64_t B, int64_t n, int64_t pitch,
+                      float *d_logmel, float *d_mfcc, float *d_stats, int32_t *d_status,
+                      float *d_clipmax, hlmc_graph **out);
+int hlmc_graph_launch(hlmc_graph *graph, void *stream);
+void hlmc_graph_destroy(hlmc_graph *graph);
+
 /* The same plus librosa.feature.chroma_stft ([R] src/1_preprocessing.py:96-101,
  * src/1_preprocessing_advanced.py:139-141; n_fft = 2048, power = 2 plans only):
  *   d_chroma : (B, 12, T) float32, each frame divided by its largest chroma bin, or NULL

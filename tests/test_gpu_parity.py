@@ -558,3 +558,24 @@ def test_fused_pooling_at_the_largest_filterbank(built):
     b = ex.extract_host(y, logmel=False, mfcc=False, stats=False, pooled=True)
     assert b["pooled"].shape == (5, 2 * 256 + 2 * 128 + 10)
     assert np.abs(a["pooled"] - b["pooled"]).max() <= 2e-5 * np.abs(a["pooled"]).max()
+
+
+def test_cuda_graph_replay_equals_the_eager_call(built):
+    """hlmc_graph_*: extract_device captured once, replayed on new audio written into the captured input buffer."""
+    import torch
+
+    hl = built
+    ex = hl.FeatureExtractor(ref=np.max, n_mfcc=40)
+    y0 = torch.from_numpy(hl.synth.synth_batch(3, 22050, seed=1)).cuda()
+    g = ex.capture_device(y0)
+    for seed in (2, 3):
+        y = torch.from_numpy(hl.synth.synth_batch(3, 22050, seed=seed)).cuda()
+        g.waves.copy_(y)
+        got = {k: v.clone() for k, v in g.replay().items()}
+        torch.cuda.synchronize()
+        want = ex.extract_device(y)
+        for k in ("logmel", "mfcc", "stats", "status"):
+            assert torch.equal(got[k], want[k]), k
+    g.close()
+    with pytest.raises(hl.ParameterError):
+        ex.capture_device(torch.zeros((0, 22050), device="cuda"))
