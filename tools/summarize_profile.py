@@ -19,6 +19,8 @@ KEYS = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "sm__cycles_elapsed.max", "smsp__warps_eligible.avg.per_cycle_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
 ]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -59,6 +61,7 @@ for k in summary:
                        "dram_bytes_per_launch": rd + wr, "dram_bytes_per_clip": (rd + wr) / clips}, f, indent=1)
         with open(os.path.join(out_dir, "frames_fast_pipes.json"), "w") as f:
             json.dump({"source": f"profiles/{tag}_ncu_summary.json (ncu --set full, one launch, {clips} clips)",
+                       "fp32_pipe_cycles_active_pct": k.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                        "fma_pipe_pct": k.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
                        "alu_pipe_pct": k.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                        "lsu_pipe_pct": k.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
