@@ -89,6 +89,23 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
+// Sixteen warp sums for the price of 1.6: a reduce-scatter butterfly.  On return lane l holds the warp total of
+// v[l >> 1] (both lanes of a pair hold the same value); the pairings and their order are those of warp_sum, so
+// each total is bitwise the one warp_sum would give.
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+        const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = up ? v[i] : v[i + w];
+            const float keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 2 * w);
+        }
+    }
+    return v[0] + __shfl_xor_sync(FULL, v[0], 1);
+}
+
 // np.pad index maps (librosa.stft / rms pad_mode; zero_crossing_rate is always "edge").
 __device__ __forceinline__ int reflect_index(int s, int n) {
     if (n == 1) return 0;
@@ -1483,64 +1500,78 @@ __device__ __forceinline__ void for_each_candidate(const float2* __restrict__ c,
     }
 }
 
-__device__ unsigned select_kth_bits(const float2* __restrict__ c, const int* __restrict__ cnt, int T, int cpf,
-                                    unsigned k, unsigned* hist, unsigned* s_misc, unsigned* s_warp) {
-    // keys: IEEE bits of the (positive) magnitudes; digits of 11 + 11 + 10 bits
-    unsigned prefix = 0u, mask = 0u;
+// Rank search in a digit histogram: every thread owns nb / kTunThreads consecutive bins; block-wide exclusive
+// scan of the per-thread sums (warp shuffles + one shared hop), then the owner of rank k walks its bins.
+// Writes the digit to out[0] and the rank inside that bin to out[1].  Contains block barriers.
+__device__ void digit_search(const unsigned* hist, int nb, unsigned k, unsigned* s_warp, unsigned* out) {
+    const int per = nb / kTunThreads;                 // 8 or 4
+    unsigned mine = 0u;
+    for (int j = 0; j < per; ++j) mine += hist[threadIdx.x * per + j];
+    unsigned incl = mine;
+    const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned tv = __shfl_up_sync(FULL, incl, d);
+        if (ln >= d) incl += tv;
+    }
+    __syncthreads();                                  // s_warp may still be read by the previous search
+    if (ln == 31) s_warp[wp] = incl;
+    __syncthreads();
+    unsigned off = 0u;
+    for (int q = 0; q < wp; ++q) off += s_warp[q];
+    const unsigned excl = off + incl - mine;
+    if (k >= excl && k < excl + mine) {
+        unsigned cum = excl;
+        int d = threadIdx.x * per;
+        for (;; ++d) {
+            if (cum + hist[d] > k) break;
+            cum += hist[d];
+        }
+        out[0] = (unsigned)d;
+        out[1] = k - cum;
+    }
+}
+
+// The k0-th and k1-th smallest magnitudes (k0 <= k1, usually adjacent: the two middle elements np.median
+// averages) by ONE radix descent: keys are the IEEE bits of the (positive) magnitudes, digits of 11 + 11 + 10
+// bits; while both ranks share their prefix one histogram serves both, afterwards each candidate is counted
+// into the histogram of the prefix it matches - three passes over the candidates in either case.
+__device__ void select_two(const float2* __restrict__ c, const int* __restrict__ cnt, int T, int cpf,
+                           unsigned k0, unsigned k1, unsigned* hist /* 2 x 2048 */, unsigned* s_misc /* 4 */,
+                           unsigned* s_warp, unsigned& bits0, unsigned& bits1) {
+    unsigned prefix0 = 0u, prefix1 = 0u, mask = 0u;
     const int shifts[3] = {21, 10, 0};
     const int widths[3] = {11, 11, 10};
     for (int lvl = 0; lvl < 3; ++lvl) {
         const int sh = shifts[lvl], nb = 1 << widths[lvl];
-        for (int i = threadIdx.x; i < nb; i += kTunThreads) hist[i] = 0u;
+        const bool split = (prefix0 != prefix1);
+        for (int i = threadIdx.x; i < nb; i += kTunThreads) { hist[i] = 0u; hist[2048 + i] = 0u; }
         __syncthreads();
         for_each_candidate(c, cnt, T, cpf, [&](const float2 pm) {
-            const unsigned key = __float_as_uint(pm.y);
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
+            const unsigned key = __float_as_uint(pm.y), pk = key & mask, d = (key >> sh) & (nb - 1);
+            if (pk == prefix0) atomicAdd(&hist[d], 1u);
+            else if (split && pk == prefix1) atomicAdd(&hist[2048 + d], 1u);
         });
         __syncthreads();
-        // digit search: every thread owns nb/256 consecutive bins; block-wide exclusive scan of the
-        // per-thread sums (warp shuffles + one shared hop), then the owner of rank k walks its bins
-        {
-            const int per = nb / kTunThreads;                 // 8 or 4
-            unsigned mine = 0u;
-            for (int j = 0; j < per; ++j) mine += hist[threadIdx.x * per + j];
-            unsigned incl = mine;
-            const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned tv = __shfl_up_sync(FULL, incl, d);
-                if (ln >= d) incl += tv;
-            }
-            if (ln == 31) s_warp[wp] = incl;
-            __syncthreads();
-            unsigned off = 0u;
-            for (int q = 0; q < wp; ++q) off += s_warp[q];
-            const unsigned excl = off + incl - mine;
-            if (k >= excl && k < excl + mine) {
-                unsigned cum = excl;
-                int d = threadIdx.x * per;
-                for (;; ++d) {
-                    if (cum + hist[d] > k) break;
-                    cum += hist[d];
-                }
-                s_misc[0] = (unsigned)d;
-                s_misc[1] = k - cum;
-            }
-        }
+        digit_search(hist, nb, k0, s_warp, s_misc);
+        digit_search(split ? hist + 2048 : hist, nb, k1, s_warp, s_misc + 2);
         __syncthreads();
-        prefix |= s_misc[0] << sh;
+        prefix0 |= s_misc[0] << sh;
+        prefix1 |= s_misc[2] << sh;
         mask |= (unsigned)(nb - 1) << sh;
-        k = s_misc[1];
+        k0 = s_misc[1];
+        k1 = s_misc[3];
         __syncthreads();
     }
-    return prefix;
+    bits0 = prefix0;
+    bits1 = prefix1;
 }
 
 __global__ void __launch_bounds__(kTunThreads)
 tuning_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_count, int T, int cpf,
               const double* __restrict__ edges, float* __restrict__ tuning, int* __restrict__ tuning_idx) {
-    __shared__ unsigned hist[2048];
-    __shared__ unsigned s_misc[2];
+    __shared__ unsigned hist[2 * 2048];
+    __shared__ unsigned s_misc[4];
     __shared__ unsigned s_warp[kTunThreads / 32];
     __shared__ unsigned counts[kTuningBins];
     __shared__ int s_n;
@@ -1562,12 +1593,11 @@ tuning_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_coun
         return;
     }
     // np.median
-    const unsigned hi_bits = select_kth_bits(c, cnt, T, cpf, (unsigned)(n / 2), hist, s_misc, s_warp);
+    unsigned lo_bits, hi_bits;
+    select_two(c, cnt, T, cpf, (unsigned)((n & 1) ? n / 2 : n / 2 - 1), (unsigned)(n / 2), hist, s_misc, s_warp,
+               lo_bits, hi_bits);
     float thr = __uint_as_float(hi_bits);
-    if ((n & 1) == 0) {
-        const unsigned lo_bits = select_kth_bits(c, cnt, T, cpf, (unsigned)(n / 2 - 1), hist, s_misc, s_warp);
-        thr = (__uint_as_float(lo_bits) + thr) * 0.5f;
-    }
+    if ((n & 1) == 0) thr = (__uint_as_float(lo_bits) + thr) * 0.5f;
     for (int i = threadIdx.x; i < kTuningBins; i += kTunThreads) counts[i] = 0u;
     __syncthreads();
     for_each_candidate(c, cnt, T, cpf, [&](const float2 pm) {
@@ -1707,7 +1737,9 @@ chroma_project(const float* __restrict__ pstash, const ChromaArgs ca, long long 
                 pb[q] = __ldg(reinterpret_cast<const float4*>(fb) + lane * 8 + q);
             }
             const float pa512 = __ldg(fa + 32 * 32), pb512 = __ldg(fb + 32 * 32);
-            float rawa[kChroma], rawb[kChroma];
+            float rawa[16], rawb[16];
+#pragma unroll
+            for (int c = kChroma; c < 16; ++c) { rawa[c] = 0.0f; rawb[c] = 0.0f; }
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) {
                 const float4* fp = reinterpret_cast<const float4*>(fbs) + (c * 8) * 32 + lane;
@@ -1726,19 +1758,16 @@ chroma_project(const float* __restrict__ pstash, const ChromaArgs ca, long long 
                     ra = fmaf(wm, pa512, ra);
                     rb = fmaf(wm, pb512, rb);
                 }
-                rawa[c] = warp_sum(ra);
-                rawb[c] = warp_sum(rb);
+                rawa[c] = ra;
+                rawb[c] = rb;
             }
-            float mxa = 0.0f, mxb = 0.0f;
-#pragma unroll
-            for (int c = 0; c < kChroma; ++c) { mxa = fmaxf(mxa, fabsf(rawa[c])); mxb = fmaxf(mxb, fabsf(rawb[c])); }
+            // lane l ends up with chroma bin l >> 1 of both frames (bins 12..15 are padding)
+            const float minea = warp_sum16(rawa, lane), mineb = warp_sum16(rawb, lane);
+            const float mxa = warp_max(fabsf(minea)), mxb = warp_max(fabsf(mineb));
             const float inva = (mxa < 1.17549435e-38f) ? 1.0f : 1.0f / mxa;   // util.normalize(norm=inf)
             const float invb = (mxb < 1.17549435e-38f) ? 1.0f : 1.0f / mxb;
-            float minea = rawa[0], mineb = rawb[0];
-#pragma unroll
-            for (int c = 1; c < kChroma; ++c) { minea = (lane == c) ? rawa[c] : minea; mineb = (lane == c) ? rawb[c] : mineb; }
-            if (lane < kChroma) {
-                float* o = ca.chroma + ((size_t)b * kChroma + lane) * T + t0;
+            if (!(lane & 1) && (lane >> 1) < kChroma) {
+                float* o = ca.chroma + ((size_t)b * kChroma + (lane >> 1)) * T + t0;
                 o[0] = minea * inva;
                 if (two) o[1] = mineb * invb;
             }
