@@ -579,3 +579,34 @@ def test_cuda_graph_replay_equals_the_eager_call(built):
     g.close()
     with pytest.raises(hl.ParameterError):
         ex.capture_device(torch.zeros((0, 22050), device="cuda"))
+
+
+def _random_cases(n_cases, seed):
+    """Seeded random parameter combinations over every kernel family (the draw is fixed, so a failure reproduces)."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n_cases):
+        n_fft = int(rng.choice([512, 1024, 2048, 2048, 2048, 4096]))
+        kw = dict(n_fft=n_fft,
+                  hop_length=int(rng.choice([n_fft // 4, n_fft // 2, n_fft // 8, int(rng.integers(50, n_fft))])),
+                  pad_mode=str(rng.choice(["constant", "reflect", "edge"])), center=bool(rng.random() < 0.8),
+                  n_mels=int(rng.choice([128, 128, 40, 64, 96, 20])), htk=bool(rng.random() < 0.25),
+                  power=float(rng.choice([2.0, 2.0, 1.0])), roll_percent=float(rng.choice([0.85, 0.5, 0.95])))
+        kw["n_mfcc"] = int(min(kw["n_mels"], rng.choice([13, 20, 40])))
+        if rng.random() < 0.3:
+            kw["window"] = str(rng.choice(["hamming", "blackman"]))
+        if rng.random() < 0.25:
+            kw["fmin"], kw["fmax"] = float(rng.choice([0.0, 50.0, 300.0])), float(rng.choice([4000.0, 8000.0, 11025.0]))
+        if rng.random() < 0.2:
+            kw["win_length"] = n_fft // 2
+        n = int(rng.choice([n_fft + int(rng.integers(0, 3 * n_fft)), int(rng.integers(2 * n_fft, 40000))]))
+        cases.append((n, int(rng.integers(0, 4)), kw))
+    return cases
+
+
+@pytest.mark.parametrize("n,pitch_extra,kw", _random_cases(36, seed=20261018))
+def test_random_parameter_combinations(built, n, pitch_extra, kw):
+    """Every kernel family against the oracle on seeded random combinations of the librosa parameters, clip
+    lengths and row pitches (mis-aligned rows take the hand-built staging path)."""
+    y = built.synth.synth_batch(5, n, seed=n)
+    _check_batch(built, y, pitch=n + pitch_extra, **kw)
