@@ -725,10 +725,11 @@ constexpr int k4Warps = 8;
 int fast4_smem_bytes(const Fast4Tables& ft) { return (((2 * k4Warps + 3) & ~3) + ft.total + k4Warps * k4WarpFloats) * 4; }
 
 // phases 1-5 of one 1024-point pass: v[j] = element lane + 32 j on entry; on exit v[i] / v[16+i] hold the
-// lane's low run k' = 16 lane + i and its partners (pass 0: 1024 - k', pass 1: 1023 - k').
-template <int PASS>
+// lane's low run k' = 16 lane + i and its partners (pass 0: 1024 - k', pass 1: 1023 - k').  `pass` is a
+// run-time value on purpose: both passes execute the SAME instructions (the kernel's code would otherwise
+// not fit the instruction cache; ncu showed 0.9 no-instruction stall cycles per issue with two copies).
 __device__ __forceinline__ void fft1024_regroup(float2 (&v)[32], float2* __restrict__ sc2,
-                                                const float2* __restrict__ s_tw1, int lane, float2& e512) {
+                                                const float2* __restrict__ s_tw1, int lane, int pass, float2& e512) {
     fftreg2::fft_dif<32>(v);
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) {
@@ -750,17 +751,13 @@ __device__ __forceinline__ void fft1024_regroup(float2 (&v)[32], float2* __restr
     const int zlo_base = 17 * lane;
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = sc2[zlo_base + i];
-    if (PASS == 0) {
-        const int zhi_base = 17 * (63 - lane) + 16, zhi0 = (lane == 0) ? 0 : 17 * (64 - lane);
-        v[16] = sc2[zhi0];
+    // partners: pass 0: k' = 1024 - 16 lane - i (i = 0 wraps to k' = 0 for lane 0); pass 1: k' = 1023 - 16 lane - i
+    const int zhi_base = 17 * (63 - lane) + 16 - pass;
+    const int zhi0 = (pass == 0) ? ((lane == 0) ? 0 : 17 * (64 - lane)) : zhi_base;
+    v[16] = sc2[zhi0];
 #pragma unroll
-        for (int i = 1; i < 16; ++i) v[16 + i] = sc2[zhi_base - i];
-        e512 = sc2[544];
-    } else {
-        const int zhi_base = 17 * (63 - lane) + 15;          // k' = 1023 - 16 lane - i
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[16 + i] = sc2[zhi_base - i];
-    }
+    for (int i = 1; i < 16; ++i) v[16 + i] = sc2[zhi_base - i];
+    e512 = sc2[544];
     __syncwarp();
 }
 
@@ -863,45 +860,49 @@ frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         }
 
         float2 v[32];
-        float2 P[16], S[16];
+        float2 P[16], So[16];                   // after the loop So holds the odd-bin magnitudes
         float2 A0, A1, A2, B0, B1, B2;          // moments of the even (A) and odd (B) bins, (low run, high run)
-        float ss;
-        int zc;
+        float ss = 0.0f, p1024 = 0.0f, s1024 = 0.0f;
+        int zc = 0;
         // even-bin halves of the lane's (up to) 4 filters.  Indexed by the rolled group loop, i.e. 16 bytes of
         // local memory: unrolling the loop to keep it in registers measured 12 % slower (code size).
         float macc[4];
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) macc[gi] = 0.0f;
+        float wmax = 0.0f;
 
-        // ================= pass 0: even bins =================
-        {
-            float2* L2 = reinterpret_cast<float2*>(sc + off);
-            const float2 zt = make_float2(zthr, zthr), quarter = make_float2(0.25f, 0.25f), half = make_float2(0.5f, 0.5f);
-            float2 ss2 = make_float2(0.f, 0.f);
-            unsigned za0 = 0u, zb0 = 0u, za1 = 0u, zb1 = 0u;
+        // The two passes share ONE copy of the transform / split / gather code (rolled loop): with two copies the
+        // kernel spent 0.9 cycles per issue waiting for instructions.
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0) {
+                // ---- even bins: a[m] = z[m] + z[m+1024]; b[m] = z[m] - z[m+1024] parked for pass 1
+                float2* L2 = reinterpret_cast<float2*>(sc + off);
+                const float2 zt = make_float2(zthr, zthr), quarter = make_float2(0.25f, 0.25f), half = make_float2(0.5f, 0.5f);
+                float2 ss2 = make_float2(0.f, 0.f);
+                unsigned za0 = 0u, zb0 = 0u, za1 = 0u, zb1 = 0u;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float2 x0 = L2[lane + 32 * j], x1 = L2[lane + 32 * j + 1024];
-                // 0.5 * hann of samples 2(lane + 32 j) + c:  0.25 - 0.25 cos(theta + 2 pi j / 64); second half = 0.5 - that
-                const float cj = -0.25f * float(fftreg::cos2pi(j, 64)), sj = 0.25f * float(fftreg::sin2pi(j, 64));
-                float2 w0;
-                if (j == 0) w0 = __ffma2_rn(hc, make_float2(cj, cj), quarter);
-                else if (j == 16) w0 = __ffma2_rn(hs, make_float2(sj, sj), quarter);
-                else w0 = __ffma2_rn(hc, make_float2(cj, cj), __ffma2_rn(hs, make_float2(sj, sj), quarter));
-                const float2 w1 = __fadd2_rn(half, make_float2(-w0.x, -w0.y));
-                ss2 = __ffma2_rn(x0, x0, ss2);
-                ss2 = __ffma2_rn(x1, x1, ss2);
-                const float2 t0 = __fadd2_rn(x0, zt), t1 = __fadd2_rn(x1, zt);
-                za0 = __funnelshift_l(__float_as_uint(t0.x), za0, 1);
-                zb0 = __funnelshift_l(__float_as_uint(t0.y), zb0, 1);
-                za1 = __funnelshift_l(__float_as_uint(t1.x), za1, 1);
-                zb1 = __funnelshift_l(__float_as_uint(t1.y), zb1, 1);
-                const float2 z0 = __fmul2_rn(x0, w0), z1 = __fmul2_rn(x1, w1);
-                v[j] = __fadd2_rn(z0, z1);
-                L2[lane + 32 * j] = __fadd2_rn(z0, make_float2(-z1.x, -z1.y));     // b (before its twiddle)
-            }
-            ss = warp_sum(ss2.x + ss2.y);
-            {
+                for (int j = 0; j < 32; ++j) {
+                    const float2 x0 = L2[lane + 32 * j], x1 = L2[lane + 32 * j + 1024];
+                    // 0.5 * hann of samples 2(lane + 32 j) + c:  0.25 - 0.25 cos(theta + 2 pi j / 64); second half = 0.5 - that
+                    const float cj = -0.25f * float(fftreg::cos2pi(j, 64)), sj = 0.25f * float(fftreg::sin2pi(j, 64));
+                    float2 w0;
+                    if (j == 0) w0 = __ffma2_rn(hc, make_float2(cj, cj), quarter);
+                    else if (j == 16) w0 = __ffma2_rn(hs, make_float2(sj, sj), quarter);
+                    else w0 = __ffma2_rn(hc, make_float2(cj, cj), __ffma2_rn(hs, make_float2(sj, sj), quarter));
+                    const float2 w1 = __fadd2_rn(half, make_float2(-w0.x, -w0.y));
+                    ss2 = __ffma2_rn(x0, x0, ss2);
+                    ss2 = __ffma2_rn(x1, x1, ss2);
+                    const float2 t0 = __fadd2_rn(x0, zt), t1 = __fadd2_rn(x1, zt);
+                    za0 = __funnelshift_l(__float_as_uint(t0.x), za0, 1);
+                    zb0 = __funnelshift_l(__float_as_uint(t0.y), zb0, 1);
+                    za1 = __funnelshift_l(__float_as_uint(t1.x), za1, 1);
+                    zb1 = __funnelshift_l(__float_as_uint(t1.y), zb1, 1);
+                    const float2 z0 = __fmul2_rn(x0, w0), z1 = __fmul2_rn(x1, w1);
+                    v[j] = __fadd2_rn(z0, z1);
+                    L2[lane + 32 * j] = __fadd2_rn(z0, make_float2(-z1.x, -z1.y));     // b (before its twiddle)
+                }
+                ss = warp_sum(ss2.x + ss2.y);
                 // rows 0..31 (first half) in word 0, rows 32..63 in word 1, row r at bit 31 - (r & 31)
                 unsigned zn0 = __shfl_sync(FULL, za0, (lane + 1) & 31);
                 unsigned zn1 = __shfl_sync(FULL, za1, (lane + 1) & 31);
@@ -910,92 +911,77 @@ frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 zc = __popc(za0 ^ zb0) + __popc(za1 ^ zb1) + __popc(zb0 ^ zn0) + __popc((zb1 ^ zn1) & m1);
                 zc = warp_sum_i(zc);
                 if (zc_edge >= 0) zc = zc_edge;
+            } else {
+                // ---- odd bins: (z[m] - z[m+1024]) * W_2048^m
+                const float2* L2 = reinterpret_cast<const float2*>(sc + off);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 bq = L2[lane + 32 * j];
+                    const float2 tw = s_tw0[lane + 32 * j];          // W_2048^m = (cos, -sin)
+                    v[j] = fftreg2::cmul(bq, tw.x, tw.y);
+                }
             }
             __syncwarp();
-        }
-        float2 e512;
-        fft1024_regroup<0>(v, scT2, s_tw1, lane, e512);
-        split_pass(v, s_base[lane], P, S, A0, A1, A2);
-        // bin 1024 (k' = 512) pairs with itself
-        const float p1024 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
-        const float s1024 = fast_sqrt(p1024);
-        // magnitudes of the even bins for rolloff's in-order search, power of the even bins for the mel gather
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { sev[lane * 33 + i] = S[i].x; sev[lane * 33 + 16 + i] = S[i].y; }
-        {
-            const bool mag = a.use_mag != 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) scT[17 * lane + i] = mag ? S[i].x : P[i].x;
-            scT[17 * (64 - lane)] = mag ? S[0].y : P[0].y;
-#pragma unroll
-            for (int i = 1; i < 16; ++i) scT[17 * (63 - lane) + 16 - i] = mag ? S[i].y : P[i].y;
-            if (lane == 31) scT[544] = mag ? s1024 : p1024;
-            scT[17 * lane + 16] = 0.0f;
-            scT[17 * (63 - lane) + 16] = 0.0f;
-            if (lane < 16) scT[1089 + lane] = 0.0f;
-            __syncwarp();
-        }
-        if (a.mel_out != nullptr) {
-            const int* meta = reinterpret_cast<const int*>(tab + ft.mel_meta[0]);
-            const float* melw = tab + ft.mel_w[0];
-            for (int gi = 0; gi < ft.n_groups; ++gi) {
-                const int n4 = meta[gi];
-                const float4* wp = reinterpret_cast<const float4*>(melw + meta[kMaxMelGroups + gi]) + lane;
-                const float* pp = scT + meta[2 * kMaxMelGroups + 32 * gi + lane];
-                float2 a01 = make_float2(0.f, 0.f), a23 = a01;
-                mel_steps(n4, wp, pp, a01, a23);
-                a01 = __fadd2_rn(a01, a23);
-                macc[gi & 3] = (gi < 4) ? a01.x + a01.y : macc[gi & 3];
-            }
-        }
-        __syncwarp();                       // the power scratch is read: the transposes of pass 1 may overwrite it
 
-        // ================= pass 1: odd bins =================
-        {
-            const float2* L2 = reinterpret_cast<const float2*>(sc + off);
+            float2 e512, S[16], M0, M1, M2;
+            fft1024_regroup(v, scT2, s_tw1, lane, pass, e512);
+            split_pass(v, s_base[32 * pass + lane], P, S, M0, M1, M2);
+            if (pass == 0) {
+                A0 = M0; A1 = M1; A2 = M2;
+                p1024 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);      // bin 1024 (k' = 512) pairs with itself
+                s1024 = fast_sqrt(p1024);
+                // magnitudes of the even bins for rolloff's in-order search
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float2 bq = L2[lane + 32 * j];
-                const float2 tw = s_tw0[lane + 32 * j];          // W_2048^m = (cos, -sin)
-                v[j] = fftreg2::cmul(bq, tw.x, tw.y);
+                for (int i = 0; i < 16; ++i) { sev[lane * 33 + i] = S[i].x; sev[lane * 33 + 16 + i] = S[i].y; }
+            } else {
+                B0 = M0; B1 = M1; B2 = M2;
             }
-            __syncwarp();
-        }
-        fft1024_regroup<1>(v, scT2, s_tw1, lane, e512);
-        float2 So[16];
-        split_pass(v, s_base[32 + lane], P, So, B0, B1, B2);
-        {
-            const bool mag = a.use_mag != 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) scT[17 * lane + i] = mag ? So[i].x : P[i].x;
+            for (int i = 0; i < 16; ++i) So[i] = S[i];
+
+            // ---- this pass's power (or magnitude) spectrum, index k', layout q(k') = k' + k'/16
+            {
+                const bool mag = a.use_mag != 0;
+                const int hb = 17 * (63 - lane) + 16 - pass;            // partner of run element i >= 1 sits at hb - i
 #pragma unroll
-            for (int i = 0; i < 16; ++i) scT[17 * (63 - lane) + 15 - i] = mag ? So[i].y : P[i].y;
-            scT[17 * lane + 16] = 0.0f;
-            scT[17 * (63 - lane) + 16] = 0.0f;
-            if (lane < 16) scT[1088 + lane] = 0.0f;
-            __syncwarp();
-        }
-        if (a.mel_out != nullptr) {
-            const int* meta = reinterpret_cast<const int*>(tab + ft.mel_meta[1]);
-            const float* melw = tab + ft.mel_w[1];
-            float wmax = 0.0f;
-            const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
-            float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
-                                            : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
-            for (int gi = 0; gi < ft.n_groups; ++gi) {
-                const int n4 = meta[gi];
-                const float4* wp = reinterpret_cast<const float4*>(melw + meta[kMaxMelGroups + gi]) + lane;
-                const float* pp = scT + meta[2 * kMaxMelGroups + 32 * gi + lane];
-                float2 a01 = make_float2(0.f, 0.f), a23 = a01;
-                mel_steps(n4, wp, pp, a01, a23);
-                a01 = __fadd2_rn(a01, a23);
-                const float acc = (a01.x + a01.y) + macc[gi & 3];
-                const int m = 32 * gi + lane;
-                if (m < a.n_mels) outb[(size_t)m * mstride] = acc;
-                wmax = fmaxf(wmax, acc);
+                for (int i = 0; i < 16; ++i) scT[17 * lane + i] = mag ? S[i].x : P[i].x;
+                scT[hb + 1 - pass] = mag ? S[0].y : P[0].y;             // pass 0: k' = 1024 - 16 lane, pass 1: 1023 - 16 lane
+#pragma unroll
+                for (int i = 1; i < 16; ++i) scT[hb - i] = mag ? S[i].y : P[i].y;
+                if (pass == 0 && lane == 31) scT[544] = mag ? s1024 : p1024;
+                scT[17 * lane + 16] = 0.0f;
+                scT[17 * (63 - lane) + 16] = 0.0f;
+                if (lane < 16) scT[1089 - pass + lane] = 0.0f;          // taps past the last bin read zeros
+                __syncwarp();
             }
-            clip_max = fmaxf(clip_max, wmax);
+            // ---- this pass's half of the mel gather
+            if (a.mel_out != nullptr) {
+                const int* meta = reinterpret_cast<const int*>(tab + ft.mel_meta[pass]);
+                const float* melw = tab + ft.mel_w[pass];
+                const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
+                float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
+                                                : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+                for (int gi = 0; gi < ft.n_groups; ++gi) {
+                    const int n4 = meta[gi];
+                    const float4* wp = reinterpret_cast<const float4*>(melw + meta[kMaxMelGroups + gi]) + lane;
+                    const float* pp = scT + meta[2 * kMaxMelGroups + 32 * gi + lane];
+                    float2 a01 = make_float2(0.f, 0.f), a23 = a01;
+                    mel_steps(n4, wp, pp, a01, a23);
+                    a01 = __fadd2_rn(a01, a23);
+                    const float part = a01.x + a01.y;
+                    if (pass == 0) {
+                        macc[gi & 3] = part;
+                    } else {
+                        const float acc = part + macc[gi & 3];
+                        const int m = 32 * gi + lane;
+                        if (m < a.n_mels) outb[(size_t)m * mstride] = acc;
+                        wmax = fmaxf(wmax, acc);
+                    }
+                }
+            }
+            __syncwarp();                       // the power scratch is read: the next transposes may overwrite it
         }
+        clip_max = fmaxf(clip_max, wmax);
 
         // ---- centroid / bandwidth: even bins k = 32 lane + 15 + 2 d (low), 2048 - 32 lane - 15 - 2 d (high);
         //      odd bins k = 32 lane + 16 + 2 d (low), 2047 - 32 lane - 15 - 2 d (high); d = i - 7.5
