@@ -615,12 +615,25 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         ft.win = 0;
         ft.tw1 = ft.win + N;
         ft.tw2 = ft.tw1 + 31 * Lg * 2;
-        ft.mel_meta = r4(ft.tw2 + 16 * Lg * 2);
+        ft.hann_cs = r4(ft.tw2 + 16 * Lg * 2);
+        ft.mel_meta = ft.hann_cs + Lg * 4;
         ft.mel_w = r4(ft.mel_meta + (int)meta.size());
         ft.total = r4(ft.mel_w + (int)melw.size());
+        ft.nowin = ft.total;
         ft.scr = 0;
+        // full-length periodic Hann: frames_sub synthesises the window (its shared-memory pipe is 83 % busy)
+        ft.hann = (p.win_length == N) ? 1 : 0;
+        for (int i = 0; window && ft.hann && i < N; ++i)
+            if (fabs(window[i] - (0.5 - 0.5 * cos(2.0 * M_PI * double(i) / double(N)))) > 1e-9) ft.hann = 0;
         std::vector<float> blob(ft.total, 0.0f);
         memcpy(&blob[ft.win], win.data(), N * 4);
+        for (int l = 0; l < Lg; ++l) {
+            const double te = 2.0 * M_PI * double(2 * l) / double(N), to = 2.0 * M_PI * double(2 * l + 1) / double(N);
+            blob[ft.hann_cs + 4 * l + 0] = float(cos(te));
+            blob[ft.hann_cs + 4 * l + 1] = float(cos(to));
+            blob[ft.hann_cs + 4 * l + 2] = float(sin(te));
+            blob[ft.hann_cs + 4 * l + 3] = float(sin(to));
+        }
         for (int k1 = 1; k1 < 32; ++k1)
             for (int l = 0; l < Lg; ++l) {
                 const double th = 2.0 * M_PI * double((l * k1) % Mh) / double(Mh);

@@ -1129,7 +1129,7 @@ int sub_smem_bytes(const FastTables& ft, int nwarps, int L) {
     return (((2 * nwarps + 3) & ~3) + ft.total + nwarps * wb) * 4;
 }
 
-template <int L, int NW>
+template <int L, int NW, bool HANN>
 __global__ void __launch_bounds__(NW * 32, 1)
 frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
     using G = SubGeom<L>;
@@ -1232,10 +1232,26 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
             const float2* xp = reinterpret_cast<const float2*>(sc + off);
             const float2 zt = make_float2(zthr, zthr);
             float2 ss2 = make_float2(0.0f, 0.0f);
+            // HANN: 0.5 * w[2 (lg + L j) + c] = 0.25 - 0.25 cos(theta_lg,c + 2 pi j / 32), synthesised as in
+            // frames_fast_2048 instead of read from the window table
+            float2 hc = make_float2(0.f, 0.f), hs = hc;
+            if (HANN) {
+                const float4 cs = reinterpret_cast<const float4*>(tab + ft.hann_cs)[lg];
+                hc = make_float2(cs.x, cs.y); hs = make_float2(cs.z, cs.w);
+            }
+            const float2 quarter = make_float2(0.25f, 0.25f);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float2 x = xp[lg + L * j];
-                const float2 w = s_win[lg + L * j];
+                float2 w;
+                if (HANN) {
+                    const float cj = -0.25f * float(fftreg::cos2pi(j, 32)), sj = 0.25f * float(fftreg::sin2pi(j, 32));
+                    if (j == 0 || j == 16) w = __ffma2_rn(hc, make_float2(cj, cj), quarter);
+                    else if (j == 8 || j == 24) w = __ffma2_rn(hs, make_float2(sj, sj), quarter);
+                    else w = __ffma2_rn(hc, make_float2(cj, cj), __ffma2_rn(hs, make_float2(sj, sj), quarter));
+                } else {
+                    w = s_win[lg + L * j];
+                }
                 ss2 = __ffma2_rn(x, x, ss2);
                 const float2 xt = __fadd2_rn(x, zt);
                 za = __funnelshift_l(__float_as_uint(xt.x), za, 1);
@@ -1446,25 +1462,28 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
     }
 }
 
-template <int L>
+template <int L, bool HANN>
 static cudaError_t launch_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
                               cudaStream_t stream) {
     constexpr int NW = 16;
     const int smem = sub_smem_bytes(ft, NW, L);
-    cudaError_t e = cudaFuncSetAttribute(frames_sub<L, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(frames_sub<L, NW, HANN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long units = (long long)a.B * ((a.T + SubGeom<L>::FW - 1) / SubGeom<L>::FW);
     if (units <= 0) return cudaSuccess;
     long long grid = (units + NW - 1) / NW;
     if (grid > num_sms) grid = num_sms;
-    frames_sub<L, NW><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    frames_sub<L, NW, HANN><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
+
 cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
                               cudaStream_t stream) {
-    if (a.n_fft == 1024) return launch_sub<16>(a, d_tables, ft, num_sms, stream);
-    if (a.n_fft == 512) return launch_sub<8>(a, d_tables, ft, num_sms, stream);
+    if (a.n_fft == 1024) return ft.hann ? launch_sub<16, true>(a, d_tables, ft, num_sms, stream)
+                                        : launch_sub<16, false>(a, d_tables, ft, num_sms, stream);
+    if (a.n_fft == 512) return ft.hann ? launch_sub<8, true>(a, d_tables, ft, num_sms, stream)
+                                       : launch_sub<8, false>(a, d_tables, ft, num_sms, stream);
     return cudaErrorInvalidValue;
 }
 
