@@ -1496,14 +1496,31 @@ cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const F
 constexpr int kTunThreads = 256;
 
 // Walks every candidate of the clip: one warp per frame, lanes over that frame's list.
+// Visits every piptrack candidate of one clip: a warp takes four frames at a time so that four independent
+// loads are in flight per lane (the kernel is bound by the latency of these loads: ncu, 12 long-scoreboard
+// stall cycles per issue with one frame at a time).
 template <class F>
 __device__ __forceinline__ void for_each_candidate(const float2* __restrict__ c, const int* __restrict__ cnt,
                                                    int T, int cpf, F f) {
     const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    for (int t = wp; t < T; t += kTunThreads / 32) {
-        const int m = cnt[t];
-        const float2* row = c + (size_t)t * cpf;
-        for (int j = ln; j < m; j += 32) f(row[j]);
+    constexpr int W = kTunThreads / 32, U = 4;
+    for (int t0 = wp; t0 < T; t0 += U * W) {
+        int m[U], mmax = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * W;
+            m[u] = (t < T) ? __ldg(cnt + t) : 0;
+            mmax = max(mmax, m[u]);
+        }
+        for (int j = ln; j < mmax; j += 32) {
+            float2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (j < m[u]) v[u] = __ldg(c + (size_t)(t0 + u * W) * cpf + j);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (j < m[u]) f(v[u]);
+        }
     }
 }
 
