@@ -23,7 +23,10 @@ EXPORTS = (
     "hlmc_chroma_workspace_bytes", "hlmc_extract_device_ex", "hlmc_pool_device_ex",
     "hlmc_extract_host_io", "hlmc_column_stats_device", "hlmc_standardize_device",
     "hlmc_extract_pooled_device", "hlmc_graph_create", "hlmc_graph_launch", "hlmc_graph_destroy",
+    "hlmc_resampled_length", "hlmc_load_frontend_device", "hlmc_resample_taps",
+    "hlmc_impute_stats_device", "hlmc_scaler_stats_f64_device", "hlmc_impute_scale_device",
 )
+ABI_VERSION = 2
 
 HLMC_OK, HLMC_ERR_PARAM, HLMC_ERR_UNSUPPORTED, HLMC_ERR_CUDA, HLMC_ERR_NOMEM = 0, -1, -2, -3, -4
 PAD_MODES = {"constant": 0, "reflect": 1, "edge": 2}
@@ -52,6 +55,10 @@ class HlmcHostIo(C.Structure):
         ("stats", C.c_void_p), ("chroma", C.c_void_p), ("tuning", C.c_void_p), ("pooled", C.c_void_p),
         ("status", C.c_void_p), ("pooled_with_chroma", C.c_int32), ("chunk_clips", C.c_int64),
         ("n_streams", C.c_int32),
+        # ABI 2
+        ("channels", C.c_int32), ("sr_in", C.c_int32), ("reserved0", C.c_int32),
+        ("fixed_logmel", C.c_void_p), ("fixed_frames", C.c_int64), ("wave_out", C.c_void_p),
+        ("valid_frames", C.c_void_p),
     ]
 
 
@@ -99,6 +106,14 @@ def _load():
     lib.hlmc_extract_host_io.argtypes = [vp, C.POINTER(HlmcHostIo)]
     lib.hlmc_column_stats_device.argtypes = [vp, i64, i64, vp, vp, C.c_int, vp]
     lib.hlmc_standardize_device.argtypes = [vp, vp, i64, i64, vp, vp, C.c_int, vp]
+    lib.hlmc_resampled_length.argtypes = [i64, i32, i32]
+    lib.hlmc_resampled_length.restype = i64
+    lib.hlmc_load_frontend_device.argtypes = [vp, vp, C.c_int, C.c_int, i64, i64, i64, i32, vp, i64, i64, vp, vp]
+    lib.hlmc_resample_taps.argtypes = [i32, i32, vp, i64]
+    lib.hlmc_resample_taps.restype = i64
+    lib.hlmc_impute_stats_device.argtypes = [vp, i64, i64, vp, vp, C.c_int, vp]
+    lib.hlmc_scaler_stats_f64_device.argtypes = [vp, i64, i64, vp, vp, vp, C.c_int, vp]
+    lib.hlmc_impute_scale_device.argtypes = [vp, i64, i64, vp, i64, vp, vp, vp, vp, vp, C.c_int, vp]
     lib.hlmc_last_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.hlmc_last_transfer_bytes.restype = None
     lib.hlmc_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -108,6 +123,8 @@ def _load():
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("hlmc_abi_version",):
             fn.restype = C.c_int
+    if lib.hlmc_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI {lib.hlmc_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
     return lib
 
 

@@ -240,9 +240,14 @@ class FeatureExtractor:
 
         def buf(key, shape, dtype=torch.float32):
             t = out.get(key)
-            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous():
+            if t is None:
                 t = torch.empty(shape, dtype=dtype, device=dev)
                 out[key] = t
+            elif (tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous()
+                  or t.device != dev):
+                # a caller-supplied buffer is a promise about where the result lands: never swap it silently
+                raise ParameterError(f"out[{key!r}] must be a contiguous {dtype} tensor of shape {tuple(shape)} "
+                                     f"on {dev}, got {t.dtype} {tuple(t.shape)} on {t.device}")
             return t
 
         logmel = buf("logmel", (B, self.n_mels, T))
@@ -360,13 +365,27 @@ class FeatureExtractor:
 
     # -- host path (the reference-facing call) ---------------------------------
     def extract_host(self, waves, *, logmel=True, mfcc=True, stats=True, status=True, pooled=False,
-                     chroma=False, chunk_clips=0, n_streams=3, out=None, pad_to=None):
+                     chroma=False, chunk_clips=0, n_streams=3, out=None, pad_to=None, fixed_frames=None,
+                     sr_in=None, wave_out=False, valid_frames=None):
         """(B, n) host float32 -- or int16 PCM -- (numpy or CPU torch, ideally pinned) -> dict of numpy arrays.
 
-        H2D copies, kernels and D2H copies are overlapped inside the C library.  int16 input is
-        converted on the device as librosa.load does for PCM16 files (x / 32768); ``pad_to`` right
-        zero-pads every clip on the device to that many samples, the scripts' ``np.pad`` to
-        ``sample_rate * duration`` ([R] src/1_preprocessing.py:146-148).
+        H2D copies, kernels and D2H copies are overlapped inside the C library.  The front end of the
+        scripts' ``load_audio_file`` ([R] src/1_preprocessing.py:137-153) runs on the device:
+
+        * int16 input is converted as librosa.load does for PCM16 files (x / 32768);
+        * a 3-D ``(B, n, channels)`` input holds interleaved frames and is averaged to mono (``librosa.to_mono``);
+        * ``sr_in`` different from the plan's ``sr`` resamples with ``librosa.resample(res_type="polyphase")``
+          (= ``scipy.signal.resample_poly``; librosa.load's default ``soxr_hq`` is a different low-pass);
+        * ``pad_to`` right zero-pads every clip to that many samples (at the plan's rate), the scripts'
+          ``np.pad`` to ``sample_rate * duration``.
+
+        ``valid_frames`` (B,) gives every clip its own frame count (files shorter than ``duration``): frames
+        past it are ignored and the clip is zero-padded after ITS resampled length.
+
+        ``fixed_frames`` adds ``fixed_logmel`` (B, n_mels, fixed_frames): the log-mel image cropped or padded
+        with its minimum ([R] src/1_preprocessing_advanced.py:108-112).  ``wave_out=True`` also returns
+        ``wave`` (B, n_total), the clips as the features saw them.  Entries of ``out`` must have exactly the
+        shape and dtype the call produces (``ParameterError`` otherwise).
         """
         tensor_in = None
         try:
@@ -389,13 +408,27 @@ class FeatureExtractor:
         esz = waves.dtype.itemsize
         if waves.ndim == 1:
             waves = waves[None]
-        if waves.ndim != 2:
-            raise ParameterError("expected (B, n) waveforms")
-        if waves.strides[1] != esz or (waves.shape[0] > 1 and (waves.strides[0] % esz or waves.strides[0] < esz * waves.shape[1])):
-            waves = np.ascontiguousarray(waves)
-        B, n = waves.shape
-        n_total = int(pad_to) if pad_to else n
-        if n_total < n:
+        channels = 1
+        if waves.ndim == 3:                       # (B, n, channels): frames interleaved as in a WAV file
+            channels = int(waves.shape[2])
+            if channels < 1:
+                raise ParameterError("expected at least one channel")
+            if not waves.flags.c_contiguous:
+                waves = np.ascontiguousarray(waves)
+        elif waves.ndim != 2:
+            raise ParameterError("expected (B, n) or (B, n, channels) waveforms")
+        fsz = esz * channels
+        if channels == 1:
+            waves = waves.reshape(waves.shape[0], waves.shape[1])
+            if waves.strides[1] != esz or (waves.shape[0] > 1 and (waves.strides[0] % esz or waves.strides[0] < esz * waves.shape[1])):
+                waves = np.ascontiguousarray(waves)
+        B, n = waves.shape[0], waves.shape[1]
+        sr_in = int(sr_in) if sr_in else 0
+        if sr_in == self.params.sr:
+            sr_in = 0
+        n_res = int(lib.hlmc_resampled_length(n, sr_in, self.params.sr)) if sr_in else n
+        n_total = int(pad_to) if pad_to else n_res
+        if n_total < n_res:
             raise ParameterError("pad_to is shorter than the clips")
         T = self.num_frames(n_total)
         mfcc = bool(mfcc) and self.n_mfcc > 0
@@ -403,9 +436,13 @@ class FeatureExtractor:
 
         def buf(key, shape, dtype=np.float32):
             a = out.get(key)
-            if a is None or a.shape != tuple(shape) or a.dtype != dtype or not a.flags.c_contiguous:
+            if a is None:
                 a = np.empty(shape, dtype=dtype)
                 out[key] = a
+            elif not (isinstance(a, np.ndarray) and a.shape == tuple(shape) and a.dtype == dtype
+                      and a.flags.c_contiguous and a.flags.writeable):
+                raise ParameterError(f"out[{key!r}] must be a writable C-contiguous {np.dtype(dtype).name} array of "
+                                     f"shape {tuple(shape)}, got {getattr(a, 'dtype', type(a))} {getattr(a, 'shape', '')}")
             return a
 
         lm = buf("logmel", (B, self.n_mels, T)) if logmel else None
@@ -415,16 +452,57 @@ class FeatureExtractor:
         po = buf("pooled", (B, self.pooled_width(self.n_mfcc > 0, bool(chroma)))) if pooled else None
         ch = buf("chroma", (B, 12, T)) if (chroma and chroma != "pooled") else None     # "pooled": columns only
         tu = buf("tuning", (B,)) if (chroma and chroma != "pooled") else None
+        fx = buf("fixed_logmel", (B, self.n_mels, int(fixed_frames))) if fixed_frames else None
+        wo = buf("wave", (B, n_total)) if wave_out else None
+        vf = None
+        if valid_frames is not None:
+            vf = np.ascontiguousarray(valid_frames, dtype=np.int64)
+            if vf.shape != (B,) or (vf < 0).any() or (vf > n).any():
+                raise ParameterError("valid_frames must be (B,) counts in [0, n]")
         ptr = lambda a: a.ctypes.data if a is not None else None
         io = HlmcHostIo(wave=ptr(waves), sample_format=1 if pcm16 else 0, B=B, n_valid=n,
-                        pitch=n if B <= 1 else waves.strides[0] // esz, n_total=n_total, logmel=ptr(lm),
+                        pitch=n if B <= 1 else waves.strides[0] // fsz, n_total=n_total, logmel=ptr(lm),
                         mfcc=ptr(mf), stats=ptr(st), chroma=ptr(ch), tuning=ptr(tu), pooled=ptr(po),
                         status=ptr(sta), pooled_with_chroma=int(bool(chroma)), chunk_clips=int(chunk_clips),
-                        n_streams=int(n_streams))
+                        n_streams=int(n_streams), channels=channels, sr_in=sr_in, reserved0=0,
+                        fixed_logmel=ptr(fx), fixed_frames=int(fixed_frames or 0), wave_out=ptr(wo),
+                        valid_frames=ptr(vf))
         with self._lock:
             _check(lib.hlmc_extract_host_io(self._plan, C.byref(io)))
         del tensor_in
         return out
+
+    def load_frontend_device(self, raw, *, sr_in=None, pad_to=None, valid_frames=None):
+        """librosa.load's arithmetic for a device-resident batch: (B, n) or (B, n, channels) CUDA int16 /
+        float32 -> (B, n_total) float32 at the plan's rate (mono mix, polyphase resampling, zero pad)."""
+        import torch
+
+        if not (isinstance(raw, torch.Tensor) and raw.is_cuda):
+            raise TypeError("expected a CUDA torch.Tensor")
+        if raw.dtype not in (torch.int16, torch.float32):
+            raise ParameterError("Audio data must be int16 PCM or float32")
+        if raw.dim() == 2:
+            raw = raw[:, :, None]
+        if raw.dim() != 3:
+            raise ParameterError("expected (B, n) or (B, n, channels)")
+        raw = raw.contiguous()
+        B, n, channels = raw.shape
+        sr_in = int(sr_in) if sr_in else 0
+        n_res = int(lib.hlmc_resampled_length(n, sr_in, self.params.sr)) if sr_in else n
+        n_total = int(pad_to) if pad_to else n_res
+        if n_total < n_res:
+            raise ParameterError("pad_to is shorter than the clips")
+        pitch = (n_total + 3) & ~3
+        store = torch.empty((B, pitch), dtype=torch.float32, device=raw.device)
+        stream = torch.cuda.current_stream(raw.device).cuda_stream
+        vf = None
+        if valid_frames is not None:
+            vf = torch.as_tensor(valid_frames, dtype=torch.int64).to(raw.device).contiguous()
+        _check(lib.hlmc_load_frontend_device(self._plan, C.c_void_p(raw.data_ptr()), 1 if raw.dtype == torch.int16 else 0,
+                                             channels, B, n, n, sr_in, C.c_void_p(store.data_ptr()), pitch, n_total,
+                                             C.c_void_p(vf.data_ptr()) if vf is not None else None,
+                                             C.c_void_p(stream)))
+        return store[:, :n_total]
 
     def last_transfer_bytes(self):
         h2d, d2h = C.c_int64(0), C.c_int64(0)
@@ -443,27 +521,47 @@ class FeatureExtractor:
         return self.extract_host(waves, **kw)
 
 
-_CACHE: dict = {}
+_CACHE: "OrderedDict" = None
 _CACHE_LOCK = threading.Lock()
+_CACHE_MAX = 32
 
 
 def get_extractor(**kw) -> FeatureExtractor:
-    """Process-wide plan cache keyed by the parameter set (plans are cheap but not free)."""
-    def freeze(v):
+    """Process-wide plan cache keyed by the parameter set (plans are cheap but not free).
+
+    Callable and array windows are keyed by the window they resolve to (two lambdas never share a plan);
+    the cache holds at most ``_CACHE_MAX`` plans and closes the least recently used one beyond that."""
+    global _CACHE
+    from collections import OrderedDict
+
+    def freeze(k, v):
+        if k == "window" and not isinstance(v, str):
+            wl = kw.get("win_length") or kw.get("n_fft", 2048)
+            w = _resolve_window(v, int(wl))
+            return ("win", None if w is None else w.tobytes())
         if isinstance(v, np.ndarray):
-            return ("nd", v.shape, v.tobytes())
+            return ("nd", v.shape, v.dtype.str, v.tobytes())
         if callable(v):
-            return ("fn", getattr(v, "__name__", repr(v)))
+            if v in (np.max, np.amax, max):
+                return ("fn", "max")
+            return ("fn", id(v))
         if isinstance(v, list):
             return tuple(v)
         return v
 
-    key = tuple(sorted((k, freeze(v)) for k, v in kw.items()))
+    key = tuple(sorted((k, freeze(k, v)) for k, v in kw.items()))
     with _CACHE_LOCK:
+        if _CACHE is None:
+            _CACHE = OrderedDict()
         ex = _CACHE.get(key)
         if ex is None:
             ex = FeatureExtractor(**kw)
             _CACHE[key] = ex
+            while len(_CACHE) > _CACHE_MAX:
+                _k, old = _CACHE.popitem(last=False)
+                old.close()
+        else:
+            _CACHE.move_to_end(key)
         return ex
 
 

@@ -35,9 +35,19 @@ struct HostPipeSlot {
     float* d_wave = nullptr; float* d_logmel = nullptr; float* d_mfcc = nullptr;
     float* d_stats = nullptr; float* d_pooled = nullptr; float* d_clipmax = nullptr;
     int32_t* d_status = nullptr;
-    int16_t* d_raw = nullptr; size_t raw_elems = 0;     // PCM16 staging (hlmc_extract_host_ex)
+    void* d_raw = nullptr; size_t raw_bytes = 0;        // staging of int16 / multi-channel / other-rate input
+    float* d_fixed = nullptr; size_t fixed_elems = 0;    // (chunk, n_mels, fixed_frames) image of the advanced script
+    long long* d_valid = nullptr; size_t valid_elems = 0; // per-clip frame counts
     float* d_melscr = nullptr;                           // frame-major mel-power scratch
     float* d_chroma = nullptr; float* d_tuning = nullptr; void* d_cwork = nullptr; size_t chroma_ws = 0;
+};
+
+// scipy.signal.resample_poly's default low-pass for one input rate, regrouped by phase for the device
+struct ResampleTaps {
+    int sr_in = 0, up = 1, down = 1, half_len = 0, n_pre_pad = 0, tpp = 0;
+    long long n_pre_remove = 0;
+    std::vector<float> h;            // firwin(...) cast to float32, times up (what scipy convolves with)
+    float* d_hpoly = nullptr;        // (up, tpp)
 };
 
 struct hlmc_plan {
@@ -63,6 +73,8 @@ struct hlmc_plan {
     // optional per-kernel timing (events recorded on the launching stream)
     int timing = 0;
     std::vector<cudaEvent_t> ev;      // triples: before frames, after frames, after db_dct
+    double t_frames_ms = 0.0, t_db_ms = 0.0; int64_t t_calls = 0;   // folded triples (the list is bounded)
+    std::vector<ResampleTaps> resamplers;   // built at first use, one per input rate
 };
 
 // ---------------------------------------------------------------------------
@@ -296,6 +308,32 @@ static int ensure_chroma_tables(hlmc_plan* pl) {
     return HLMC_OK;
 }
 
+static void free_slots(hlmc_plan* pl) {
+    for (auto& s : pl->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
+        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr);
+        cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork); cudaFree(s.d_fixed); cudaFree(s.d_valid);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    pl->slots.clear();
+    pl->slot_chunk = 0; pl->slot_n = -1; pl->slot_flags = 0;
+}
+
+// Fold finished timing triples into the running totals (keeps plan->ev bounded while timing is on).
+static int fold_timing(hlmc_plan* plan) {
+    for (size_t i = 0; i + 2 < plan->ev.size(); i += 3) {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventSynchronize(plan->ev[i + 2]));
+        CK(cudaEventElapsedTime(&a, plan->ev[i], plan->ev[i + 1]));
+        CK(cudaEventElapsedTime(&b, plan->ev[i + 1], plan->ev[i + 2]));
+        plan->t_frames_ms += a; plan->t_db_ms += b; ++plan->t_calls;
+    }
+    for (auto e : plan->ev) cudaEventDestroy(e);
+    plan->ev.clear();
+    return HLMC_OK;
+}
+
 extern "C" {
 
 int hlmc_abi_version(void) { return HLMC_ABI_VERSION; }
@@ -324,12 +362,9 @@ int64_t hlmc_num_frames(const hlmc_params* p, int64_t n) {
 void hlmc_plan_destroy(hlmc_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
-    for (auto& s : plan->slots) {
-        if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr); cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork);
-        if (s.stream) cudaStreamDestroy(s.stream);
-    }
+    free_slots(plan);
+    for (auto e : plan->ev) cudaEventDestroy(e);
+    for (auto& r : plan->resamplers) cudaFree(r.d_hpoly);
     cudaFree(plan->d_fast); cudaFree(plan->d_fast4); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
     cudaFree(plan->d_mel_lo); cudaFree(plan->d_mel_len); cudaFree(plan->d_mel_off); cudaFree(plan->d_mel_w);
     cudaFree(plan->d_dct_t); cudaFree(plan->d_chroma_fb); cudaFree(plan->d_edges);
@@ -746,11 +781,42 @@ int64_t hlmc_chroma_workspace_bytes(hlmc_plan* plan, int64_t B, int64_t n) {
 
 // d_pooled with d_logmel == NULL selects the fused path: dB, DCT and time pooling in one kernel, the
 // (B, n_mels, T) / (B, n_mfcc, T) arrays are never written.
+struct ImplOwned {                   // what one extract_device call creates before it can fail
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    float* melscr = nullptr;         // stream-ordered scratch, if the caller passed none
+    bool handed_over = false;        // events now belong to plan->ev
+};
+
+static int extract_device_body(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                               float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
+                               float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
+                               int64_t work_bytes, void* stream, float* d_melscr,
+                               float* d_pooled, int pool_mfcc, int pool_chroma, ImplOwned& own);
+
 static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
                                float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
                                float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
                                int64_t work_bytes, void* stream, float* d_melscr,
                                float* d_pooled = nullptr, int pool_mfcc = 0, int pool_chroma = 0) {
+    ImplOwned own;
+    const int rc = extract_device_body(plan, d_wave, B, n, pitch, d_logmel, d_mfcc, d_stats, d_status, d_clipmax,
+                                       d_chroma, d_tuning, d_work, work_bytes, stream, d_melscr, d_pooled, pool_mfcc,
+                                       pool_chroma, own);
+    if (rc != HLMC_OK) {             // nothing of a failed call outlives it
+        const std::string msg = g_err;
+        if (own.melscr) cudaFreeAsync(own.melscr, static_cast<cudaStream_t>(stream));
+        if (!own.handed_over)
+            for (auto e : own.ev) if (e) cudaEventDestroy(e);
+        g_err = msg;
+    }
+    return rc;
+}
+
+static int extract_device_body(hlmc_plan* plan, const float* d_wave, int64_t B, int64_t n, int64_t pitch,
+                               float* d_logmel, float* d_mfcc, float* d_stats, int32_t* d_status,
+                               float* d_clipmax, float* d_chroma, float* d_tuning, void* d_work,
+                               int64_t work_bytes, void* stream, float* d_melscr,
+                               float* d_pooled, int pool_mfcc, int pool_chroma, ImplOwned& own) {
     int64_t T;
     int rc = check_batch(plan, d_wave, B, n, pitch, &T);
     if (rc != HLMC_OK) return rc;
@@ -781,18 +847,18 @@ static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, 
         if (work_bytes >= (int64_t)(core + (size_t)B * T * kStashFloats * 4))
             pstash = reinterpret_cast<float*>(wsp + core);
     }
-    cudaEvent_t ev3[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t (&ev3)[3] = own.ev;
     if (plan->timing) {
+        if (plan->ev.size() >= 3 * 1024) { rc = fold_timing(plan); if (rc != HLMC_OK) return rc; }
         for (auto& e : ev3) CK(cudaEventCreate(&e));
         CK(cudaMemsetAsync(d_clipmax, 0, (size_t)B * 4, st));   // keep the memsets out of the bracket
     }
     if (plan->timing) CK(cudaEventRecord(ev3[0], st));
     // The frames kernel writes the mel power frame-major (each frame's n_mels values contiguous:
     // full-sector coalesced stores) into a scratch; db_dct reads it back and writes librosa's layout.
-    bool own_scr = false;
     if (!d_melscr) {
-        CK(cudaMallocAsync((void**)&d_melscr, (size_t)B * T * plan->p.n_mels * 4, st));
-        own_scr = true;
+        CK(cudaMallocAsync((void**)&own.melscr, (size_t)B * T * plan->p.n_mels * 4, st));
+        d_melscr = own.melscr;
     }
     rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_melscr, d_stats, d_status, d_clipmax, nullptr, st,
                     cand, cand_count, cand_cap, 1, pstash);
@@ -827,8 +893,9 @@ static int extract_device_impl(hlmc_plan* plan, const float* d_wave, int64_t B, 
     if (plan->timing) {
         CK(cudaEventRecord(ev3[2], st));
         for (auto& e : ev3) plan->ev.push_back(e);
+        own.handed_over = true;
     }
-    if (own_scr) CK(cudaFreeAsync(d_melscr, st));
+    if (own.melscr) { float* m = own.melscr; own.melscr = nullptr; CK(cudaFreeAsync(m, st)); }
     if (d_chroma && !fused) { rc = run_chroma(); if (rc != HLMC_OK) return rc; }
     return HLMC_OK;
 }
@@ -927,17 +994,11 @@ int hlmc_plan_set_timing(hlmc_plan* plan, int enable) {
 
 int hlmc_plan_read_timing(hlmc_plan* plan, double* frames_ms, double* db_ms, int64_t* calls) {
     if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
-    double f = 0.0, d = 0.0;
-    int64_t n = 0;
-    for (size_t i = 0; i + 2 < plan->ev.size(); i += 3) {
-        float a = 0.f, b = 0.f;
-        CK(cudaEventSynchronize(plan->ev[i + 2]));
-        CK(cudaEventElapsedTime(&a, plan->ev[i], plan->ev[i + 1]));
-        CK(cudaEventElapsedTime(&b, plan->ev[i + 1], plan->ev[i + 2]));
-        f += a; d += b; ++n;
-    }
-    for (auto e : plan->ev) cudaEventDestroy(e);
-    plan->ev.clear();
+    int rc = fold_timing(plan);
+    if (rc != HLMC_OK) return rc;
+    const double f = plan->t_frames_ms, d = plan->t_db_ms;
+    const int64_t n = plan->t_calls;
+    plan->t_frames_ms = plan->t_db_ms = 0.0; plan->t_calls = 0;
     if (frames_ms) *frames_ms = f;
     if (db_ms) *db_ms = d;
     if (calls) *calls = n;
@@ -1011,16 +1072,7 @@ int hlmc_fix_frames_device(const float* d_in, float* d_out, int64_t B, int64_t r
 // ---------------------------------------------------------------------------
 // Host pipeline: chunk the batch; H2D | kernels | D2H overlap across streams.
 // ---------------------------------------------------------------------------
-static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, int64_t T, int flags) {
-    if ((int)pl->slots.size() == n_streams && pl->slot_chunk >= chunk && pl->slot_n == n &&
-        (pl->slot_flags & flags) == flags)
-        return HLMC_OK;
-    for (auto& s : pl->slots) {
-        if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_wave); cudaFree(s.d_logmel); cudaFree(s.d_mfcc); cudaFree(s.d_stats);
-        cudaFree(s.d_pooled); cudaFree(s.d_clipmax); cudaFree(s.d_status); cudaFree(s.d_raw); cudaFree(s.d_melscr); cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork);
-        if (s.stream) cudaStreamDestroy(s.stream);
-    }
+static int alloc_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, int64_t T) {
     pl->slots.assign(n_streams, HostPipeSlot());
     const int64_t dp = (n + 3) & ~int64_t(3);
     const int nm = pl->p.n_mels, nc = pl->p.n_mfcc;
@@ -1035,20 +1087,136 @@ static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, 
         CK(cudaMalloc((void**)&s.d_clipmax, (size_t)chunk * 4));
         CK(cudaMalloc((void**)&s.d_status, (size_t)chunk * 4));
     }
+    return HLMC_OK;
+}
+
+static int ensure_slots(hlmc_plan* pl, int n_streams, int64_t chunk, int64_t n, int64_t T, int flags) {
+    if ((int)pl->slots.size() == n_streams && pl->slot_chunk >= chunk && pl->slot_n == n &&
+        (pl->slot_flags & flags) == flags)
+        return HLMC_OK;
+    free_slots(pl);                 // also marks the cache empty: a failed allocation below can never be
+                                    // mistaken for a valid configuration by a later call
+    const int rc = alloc_slots(pl, n_streams, chunk, n, T);
+    if (rc != HLMC_OK) {
+        const std::string msg = g_err;
+        free_slots(pl);
+        cudaGetLastError();
+        g_err = msg;
+        return rc;
+    }
     pl->slot_chunk = chunk; pl->slot_n = n; pl->slot_flags = flags;
     return HLMC_OK;
 }
 
-int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
-    if (!plan || !io) return fail(HLMC_ERR_PARAM, "null argument");
+static int host_io_body(hlmc_plan* plan, const hlmc_host_io* io);
+
+// ---------------------------------------------------------------------------
+// scipy.signal.resample_poly's filter (librosa.resample(res_type="polyphase")), built in float64:
+//   h = firwin(2*half_len + 1, 1/max(up, down), window=("kaiser", 5.0)), half_len = 10*max(up, down),
+//   cast to float32, times up.
+// ---------------------------------------------------------------------------
+static double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0;
+    const double q = 0.25 * x * x;
+    for (int k = 1; k < 200; ++k) {
+        term *= q / (double(k) * double(k));
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; }
+
+static void build_resample_filter(int sr_in, int sr_out, ResampleTaps& r) {
+    const int64_t g = gcd64(sr_in, sr_out);
+    r.sr_in = sr_in; r.up = (int)(sr_out / g); r.down = (int)(sr_in / g);
+    const int max_rate = std::max(r.up, r.down);
+    const double f_c = 1.0 / max_rate;
+    r.half_len = 10 * max_rate;
+    const int numtaps = 2 * r.half_len + 1;
+    std::vector<double> h(numtaps);
+    const double alpha = 0.5 * (numtaps - 1), beta = 5.0, i0b = bessel_i0(beta);
+    long double sum = 0.0L;
+    for (int k = 0; k < numtaps; ++k) {
+        const double m = k - alpha;
+        const double x = f_c * m;
+        const double sinc = (x == 0.0) ? 1.0 : sin(M_PI * x) / (M_PI * x);
+        const double rel = (k - alpha) / alpha;
+        const double win = bessel_i0(beta * sqrt(std::max(0.0, 1.0 - rel * rel))) / i0b;
+        h[k] = f_c * sinc * win;
+        sum += h[k];
+    }
+    r.h.resize(numtaps);
+    for (int k = 0; k < numtaps; ++k) {
+        const float hf = (float)(h[k] / (double)sum);        // scipy: float64 design cast to x's dtype ...
+        r.h[k] = hf * (float)r.up;                           // ... then h *= up in that dtype
+    }
+    r.n_pre_pad = r.down - r.half_len % r.down;
+    r.n_pre_remove = (r.half_len + r.n_pre_pad) / r.down;
+    r.tpp = (numtaps + r.up - 1) / r.up;
+}
+
+static int get_resampler(hlmc_plan* pl, int sr_in, const ResampleTaps** out) {
+    for (auto& r : pl->resamplers) if (r.sr_in == sr_in) { *out = &r; return HLMC_OK; }
+    if (sr_in <= 0 || sr_in > 768000) return fail(HLMC_ERR_PARAM, "bad input sample rate");
+    ResampleTaps r;
+    build_resample_filter(sr_in, pl->p.sr, r);
+    if ((int64_t)r.up * r.tpp > (int64_t(1) << 24)) return fail(HLMC_ERR_UNSUPPORTED, "resampling ratio too fine");
+    std::vector<float> poly((size_t)r.up * r.tpp, 0.0f);
+    for (int p = 0; p < r.up; ++p)
+        for (int t = 0; t < r.tpp; ++t) {
+            const int64_t q = p + (int64_t)t * r.up;
+            if (q < (int64_t)r.h.size()) poly[(size_t)p * r.tpp + t] = r.h[q];
+        }
+    CK(cudaMalloc((void**)&r.d_hpoly, poly.size() * 4));
+    CK(cudaMemcpy(r.d_hpoly, poly.data(), poly.size() * 4, cudaMemcpyHostToDevice));
+    pl->resamplers.push_back(r);
+    *out = &pl->resamplers.back();
+    return HLMC_OK;
+}
+
+static int64_t resampled_length(int64_t n_in, int64_t sr_in, int64_t sr_out) {
+    if (sr_in <= 0 || sr_in == sr_out) return n_in;
+    const int64_t g = gcd64(sr_in, sr_out);
+    const int64_t up = sr_out / g, down = sr_in / g;
+    return (n_in * up + down - 1) / down;          // resample_poly's n_out == librosa's ceil(n * ratio)
+}
+
+static int run_frontend(hlmc_plan* plan, const void* d_raw, int fmt, int channels, int64_t B, int64_t n_in,
+                        int64_t raw_pitch, int sr_in, float* d_wave, int64_t pitch, int64_t n_total,
+                        cudaStream_t st, const long long* d_valid = nullptr) {
+    FrontArgs a{};
+    a.valid = d_valid;
+    a.raw = d_raw; a.fmt = fmt; a.channels = channels < 1 ? 1 : channels; a.B = B; a.raw_pitch = raw_pitch;
+    a.n_in = n_in; a.out = d_wave; a.pitch = pitch; a.n_total = n_total; a.up = a.down = 1;
+    a.n_out = n_in;
+    if (sr_in > 0 && sr_in != plan->p.sr) {
+        const ResampleTaps* r = nullptr;
+        const int rc = get_resampler(plan, sr_in, &r);
+        if (rc != HLMC_OK) return rc;
+        a.up = r->up; a.down = r->down; a.n_pre_pad = r->n_pre_pad; a.n_pre_remove = r->n_pre_remove;
+        a.tpp = r->tpp; a.hpoly = r->d_hpoly;
+        a.n_out = resampled_length(n_in, sr_in, plan->p.sr);
+    }
+    if (a.n_out > n_total) a.n_out = n_total;
+    CK(launch_frontend(a, plan->num_sms, st));
+    return HLMC_OK;
+}
+
+static int host_io_body(hlmc_plan* plan, const hlmc_host_io* io) {
     const int sample_format = io->sample_format;
+    const int channels = io->channels > 1 ? io->channels : 1;
+    const int sr_in = (io->sr_in > 0 && io->sr_in != plan->p.sr) ? io->sr_in : 0;
     const int64_t B = io->B, n_valid = io->n_valid, h_pitch = io->pitch;
-    const int64_t n_total = io->n_total > 0 ? io->n_total : io->n_valid;
-    int64_t chunk_clips = io->chunk_clips;
-    int n_streams = io->n_streams;
     if (sample_format != HLMC_SAMPLES_F32 && sample_format != HLMC_SAMPLES_PCM16)
         return fail(HLMC_ERR_PARAM, "unknown sample_format");
-    if (n_total < n_valid) return fail(HLMC_ERR_PARAM, "n_total < n_valid");
+    if (channels > 64) return fail(HLMC_ERR_PARAM, "more than 64 channels");
+    if (n_valid < 1) return fail(HLMC_ERR_PARAM, "Input is too short");
+    const int64_t n_res = resampled_length(n_valid, sr_in, plan->p.sr);
+    const int64_t n_total = io->n_total > 0 ? io->n_total : n_res;
+    int64_t chunk_clips = io->chunk_clips;
+    int n_streams = io->n_streams;
+    if (n_total < n_res) return fail(HLMC_ERR_PARAM, "n_total is shorter than the (resampled) clips");
     int64_t T;
     const int64_t n = n_total;
     if (h_pitch < n_valid) return fail(HLMC_ERR_PARAM, "pitch < n");
@@ -1057,6 +1225,7 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
     plan->last_h2d = plan->last_d2h = 0;
     if (B == 0) return HLMC_OK;
     if (io->mfcc && plan->p.n_mfcc <= 0) return fail(HLMC_ERR_PARAM, "plan was created with n_mfcc = 0");
+    if (io->fixed_logmel && io->fixed_frames <= 0) return fail(HLMC_ERR_PARAM, "fixed_frames must be positive");
     const bool want_chroma = io->chroma || io->tuning || (io->pooled && io->pooled_with_chroma);
     if (want_chroma) {
         rc = ensure_chroma_tables(plan);
@@ -1069,36 +1238,52 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
         chunk_clips = (int64_t(64) << 20) / (n * 4);
         if (chunk_clips < 1) chunk_clips = 1;
     }
+    if (chunk_clips > 65535) chunk_clips = 65535;           // gridDim.y of the per-clip helper kernels
     if (chunk_clips > B) chunk_clips = B;
     rc = ensure_slots(plan, n_streams, chunk_clips, n, T, 0);
     if (rc != HLMC_OK) return rc;
+    const bool pcm = (sample_format == HLMC_SAMPLES_PCM16);
+    const size_t esz = pcm ? 2 : 4;
+    const bool front = (channels > 1) || (sr_in != 0) || (io->valid_frames != nullptr);   // front-end kernel needed
     // device row pitch: every row 16-byte aligned - or, for float32 rows of even length that need no pad, the
     // host layout itself (rows 8-byte aligned, which the TMA staging handles), so that the H2D copy is one
     // linear transfer instead of a pitched 2-D one
-    const bool linear = (sample_format == HLMC_SAMPLES_F32) && (n % 2 == 0) && (n_valid == n) && (h_pitch == n);
+    const bool linear = !front && !pcm && (n % 2 == 0) && (n_valid == n) && (h_pitch == n);
     const int64_t dp = linear ? n : ((n + 3) & ~int64_t(3));
-    const int64_t rp = (n_valid + 7) & ~int64_t(7);           // PCM16 staging pitch (16-B rows)
-    const bool pcm = (sample_format == HLMC_SAMPLES_PCM16);
-    const size_t esz = pcm ? 2 : 4;
+    const int64_t rp = (n_valid + 7) & ~int64_t(7);           // staging pitch in frames (16-byte rows)
+    const size_t frame_bytes = (size_t)channels * esz;
     int64_t chroma_ws = 0;
     for (auto& s : plan->slots) {
-        if (pcm && s.raw_elems < (size_t)(plan->slot_chunk * rp)) {
+        const size_t need_raw = (pcm || front) ? (size_t)plan->slot_chunk * rp * frame_bytes : 0;
+        if (s.raw_bytes < need_raw) {
             cudaFree(s.d_raw);
-            s.d_raw = nullptr;
-            CK(cudaMalloc((void**)&s.d_raw, (size_t)plan->slot_chunk * rp * 2));
-            s.raw_elems = (size_t)plan->slot_chunk * rp;
+            s.d_raw = nullptr; s.raw_bytes = 0;
+            CK(cudaMalloc(&s.d_raw, need_raw));
+            s.raw_bytes = need_raw;
+        }
+        if (io->valid_frames && s.valid_elems < (size_t)plan->slot_chunk) {
+            cudaFree(s.d_valid);
+            s.d_valid = nullptr; s.valid_elems = 0;
+            CK(cudaMalloc((void**)&s.d_valid, (size_t)plan->slot_chunk * 8));
+            s.valid_elems = (size_t)plan->slot_chunk;
+        }
+        const size_t need_fixed = io->fixed_logmel ? (size_t)plan->slot_chunk * plan->p.n_mels * io->fixed_frames : 0;
+        if (s.fixed_elems < need_fixed) {
+            cudaFree(s.d_fixed);
+            s.d_fixed = nullptr; s.fixed_elems = 0;
+            CK(cudaMalloc((void**)&s.d_fixed, need_fixed * 4));
+            s.fixed_elems = need_fixed;
         }
         if (want_chroma) {
             chroma_ws = hlmc_chroma_workspace_bytes(plan, plan->slot_chunk, n);
             if (chroma_ws < 0) return (int)chroma_ws;
             if (s.chroma_ws < (size_t)chroma_ws) {
-                cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork);
-                s.d_chroma = nullptr; s.d_tuning = nullptr; s.d_cwork = nullptr;
+                cudaFree(s.d_chroma); cudaFree(s.d_tuning); cudaFree(s.d_cwork); cudaFree(s.d_pooled);
+                s.d_chroma = nullptr; s.d_tuning = nullptr; s.d_cwork = nullptr; s.d_pooled = nullptr;
+                s.chroma_ws = 0;
                 CK(cudaMalloc((void**)&s.d_chroma, (size_t)plan->slot_chunk * kChroma * T * 4));
                 CK(cudaMalloc((void**)&s.d_tuning, (size_t)plan->slot_chunk * 4));
                 CK(cudaMalloc((void**)&s.d_cwork, (size_t)chroma_ws));
-                CK(cudaFree(s.d_pooled));
-                s.d_pooled = nullptr;
                 CK(cudaMalloc((void**)&s.d_pooled, (size_t)plan->slot_chunk *
                                                        (2 * plan->p.n_mels + 2 * plan->p.n_mfcc + 10 + 2 * kChroma) * 4));
                 s.chroma_ws = (size_t)chroma_ws;
@@ -1109,16 +1294,26 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
     const bool want_mfcc = (io->mfcc != nullptr) || (io->pooled != nullptr && nc > 0);
     const bool pool_chroma = io->pooled && io->pooled_with_chroma;
     const int pooled_w = 2 * nm + 2 * (want_mfcc ? nc : 0) + 10 + (pool_chroma ? 2 * kChroma : 0);
+    const int64_t fixed = io->fixed_frames;
     int64_t done = 0;
     for (int64_t i = 0; done < B; ++i) {
         HostPipeSlot& s = plan->slots[i % n_streams];
         const int64_t c = (B - done < chunk_clips) ? (B - done) : chunk_clips;
-        const char* src = static_cast<const char*>(io->wave) + (size_t)done * h_pitch * esz;
-        if (pcm) {
+        const char* src = static_cast<const char*>(io->wave) + (size_t)done * h_pitch * frame_bytes;
+        if (front) {
+            // [R] librosa.load: decode -> to_mono -> resample; then the scripts' zero pad, all on the device
+            CK(cudaMemcpy2DAsync(s.d_raw, (size_t)rp * frame_bytes, src, (size_t)h_pitch * frame_bytes,
+                                 (size_t)n_valid * frame_bytes, (size_t)c, cudaMemcpyHostToDevice, s.stream));
+            if (io->valid_frames)
+                CK(cudaMemcpyAsync(s.d_valid, io->valid_frames + done, (size_t)c * 8, cudaMemcpyHostToDevice, s.stream));
+            rc = run_frontend(plan, s.d_raw, pcm ? 1 : 0, channels, c, n_valid, rp, sr_in, s.d_wave, dp, n, s.stream,
+                              io->valid_frames ? s.d_valid : nullptr);
+            if (rc != HLMC_OK) return rc;
+        } else if (pcm) {
             // [R] librosa.load on a PCM16 file: float32 = int16 / 32768; then the scripts' zero pad
             CK(cudaMemcpy2DAsync(s.d_raw, (size_t)rp * 2, src, (size_t)h_pitch * 2, (size_t)n_valid * 2,
                                  (size_t)c, cudaMemcpyHostToDevice, s.stream));
-            CK(launch_pcm16_to_f32(s.d_raw, rp, s.d_wave, dp, c, n_valid, n, s.stream));
+            CK(launch_pcm16_to_f32(static_cast<const int16_t*>(s.d_raw), rp, s.d_wave, dp, c, n_valid, n, s.stream));
         } else if (linear) {
             CK(cudaMemcpyAsync(s.d_wave, src, (size_t)c * n * 4, cudaMemcpyHostToDevice, s.stream));
         } else {
@@ -1128,9 +1323,10 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
                 CK(cudaMemset2DAsync(s.d_wave + n_valid, (size_t)dp * 4, 0, (size_t)(n - n_valid) * 4,
                                      (size_t)c, s.stream));
         }
-        plan->last_h2d += c * n_valid * (int64_t)esz;
+        plan->last_h2d += c * n_valid * (int64_t)frame_bytes;
         // only pooled columns wanted: dB + DCT + pooling fused, no log-mel / MFCC arrays in HBM
-        const bool fused = io->pooled && !io->logmel && !io->mfcc && db_pool_fits(nm, want_mfcc ? plan->ncp : 0, (int)T);
+        const bool fused = io->pooled && !io->logmel && !io->mfcc && !io->fixed_logmel &&
+                           db_pool_fits(nm, want_mfcc ? plan->ncp : 0, (int)T);
         rc = extract_device_impl(plan, s.d_wave, c, n, dp, fused ? nullptr : s.d_logmel,
                                  (want_mfcc && !fused) ? s.d_mfcc : nullptr,
                                  s.d_stats, s.d_status, s.d_clipmax, want_chroma ? s.d_chroma : nullptr,
@@ -1148,16 +1344,40 @@ int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
                                c, nm, nc, (int)T, s.d_pooled, s.stream));
             CK(d2h(io->pooled + done * pooled_w, s.d_pooled, (size_t)c * pooled_w * 4));
         }
+        if (io->fixed_logmel) {
+            // [R] src/1_preprocessing_advanced.py:108-112: crop to fixed frames / pad with the clip's minimum
+            CK(launch_fix_frames(s.d_logmel, s.d_fixed, c, nm, (int)T, (int)fixed, s.stream));
+            CK(d2h(io->fixed_logmel + done * nm * fixed, s.d_fixed, (size_t)c * nm * fixed * 4));
+        }
         if (io->logmel) CK(d2h(io->logmel + done * nm * T, s.d_logmel, (size_t)c * nm * T * 4));
         if (io->mfcc) CK(d2h(io->mfcc + done * nc * T, s.d_mfcc, (size_t)c * nc * T * 4));
         if (io->stats) CK(d2h(io->stats + done * 5 * T, s.d_stats, (size_t)c * 5 * T * 4));
         if (io->chroma) CK(d2h(io->chroma + done * kChroma * T, s.d_chroma, (size_t)c * kChroma * T * 4));
         if (io->tuning) CK(d2h(io->tuning + done, s.d_tuning, (size_t)c * 4));
         if (io->status) CK(d2h(io->status + done, s.d_status, (size_t)c * 4));
+        if (io->wave_out) {
+            plan->last_d2h += c * n * 4;
+            CK(cudaMemcpy2DAsync(io->wave_out + done * n, (size_t)n * 4, s.d_wave, (size_t)dp * 4, (size_t)n * 4,
+                                 (size_t)c, cudaMemcpyDeviceToHost, s.stream));
+        }
         done += c;
     }
     for (auto& s : plan->slots) CK(cudaStreamSynchronize(s.stream));
     return HLMC_OK;
+}
+
+int hlmc_extract_host_io(hlmc_plan* plan, const hlmc_host_io* io) {
+    if (!plan || !io) return fail(HLMC_ERR_PARAM, "null argument");
+    const int rc = host_io_body(plan, io);
+    if (rc != HLMC_OK) {
+        // work may already be queued (async copies into the caller's buffers included): drain it before
+        // the caller sees the error and frees or reuses them
+        const std::string msg = g_err;
+        for (auto& s : plan->slots) if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaGetLastError();
+        g_err = msg;
+    }
+    return rc;
 }
 
 int hlmc_extract_host_ex(hlmc_plan* plan, const void* h_wave, int sample_format, int64_t B,
@@ -1194,6 +1414,77 @@ int hlmc_standardize_device(const float* d_x, float* d_y, int64_t N, int64_t D, 
     if (N < 0 || D < 0) return fail(HLMC_ERR_PARAM, "negative shape");
     CK(cudaSetDevice(device));
     CK(launch_standardize(d_x, d_y, N, D, d_mean, d_scale, static_cast<cudaStream_t>(stream)));
+    return HLMC_OK;
+}
+
+int64_t hlmc_resampled_length(int64_t n_in, int32_t sr_in, int32_t sr_out) {
+    if (n_in < 0 || sr_in < 0 || sr_out <= 0) return fail(HLMC_ERR_PARAM, "bad argument");
+    return resampled_length(n_in, sr_in, sr_out);
+}
+
+int hlmc_load_frontend_device(hlmc_plan* plan, const void* d_raw, int sample_format, int channels, int64_t B,
+                              int64_t n_in, int64_t raw_pitch, int32_t sr_in, float* d_wave, int64_t pitch,
+                              int64_t n_total, const int64_t* d_valid_frames, void* stream) {
+    if (!plan || !d_raw || !d_wave) return fail(HLMC_ERR_PARAM, "null argument");
+    if (sample_format != HLMC_SAMPLES_F32 && sample_format != HLMC_SAMPLES_PCM16)
+        return fail(HLMC_ERR_PARAM, "unknown sample_format");
+    if (channels < 1 || channels > 64) return fail(HLMC_ERR_PARAM, "bad channel count");
+    if (B < 0 || n_in < 1 || raw_pitch < n_in || pitch < n_total) return fail(HLMC_ERR_PARAM, "bad shape");
+    const int sr = (sr_in > 0 && sr_in != plan->p.sr) ? sr_in : 0;
+    if (n_total < resampled_length(n_in, sr, plan->p.sr))
+        return fail(HLMC_ERR_PARAM, "n_total is shorter than the (resampled) clips");
+    if (channels == 2 && ((reinterpret_cast<uintptr_t>(d_raw) | (size_t)raw_pitch * 2 * (sample_format ? 2 : 4)) &
+                          (sample_format ? 3 : 7)))
+        return fail(HLMC_ERR_PARAM, "stereo rows must be aligned to one frame");
+    if (B == 0) return HLMC_OK;
+    CK(cudaSetDevice(plan->device));
+    return run_frontend(plan, d_raw, sample_format == HLMC_SAMPLES_PCM16 ? 1 : 0, channels, B, n_in, raw_pitch, sr,
+                        d_wave, pitch, n_total, static_cast<cudaStream_t>(stream),
+                        reinterpret_cast<const long long*>(d_valid_frames));
+}
+
+int64_t hlmc_resample_taps(int32_t sr_in, int32_t sr_out, float* h_out, int64_t cap) {
+    if (sr_in <= 0 || sr_out <= 0 || sr_in > 768000 || sr_out > 768000) return fail(HLMC_ERR_PARAM, "bad sample rate");
+    ResampleTaps r;
+    build_resample_filter(sr_in, sr_out, r);
+    const int64_t nt = (int64_t)r.h.size();
+    if (h_out) memcpy(h_out, r.h.data(), (size_t)std::min(nt, cap < 0 ? int64_t(0) : cap) * 4);
+    return nt;
+}
+
+int hlmc_impute_stats_device(const double* d_x, int64_t N, int64_t D, double* d_sum, int64_t* d_count,
+                             int device, void* stream) {
+    if (!d_sum || !d_count || (N > 0 && D > 0 && !d_x)) return fail(HLMC_ERR_PARAM, "null argument");
+    if (N < 0 || D < 0) return fail(HLMC_ERR_PARAM, "negative shape");
+    CK(cudaSetDevice(device));
+    CK(launch_impute_stats(d_x, N, D, d_sum, reinterpret_cast<long long*>(d_count), static_cast<cudaStream_t>(stream)));
+    return HLMC_OK;
+}
+
+int hlmc_scaler_stats_f64_device(const double* d_x, int64_t N, int64_t D, const double* d_fill, double* d_mean,
+                                 double* d_m2, int device, void* stream) {
+    if (!d_mean || !d_m2 || (N > 0 && D > 0 && !d_x)) return fail(HLMC_ERR_PARAM, "null argument");
+    if (N < 0 || D < 0) return fail(HLMC_ERR_PARAM, "negative shape");
+    if (D == 0) return HLMC_OK;
+    CK(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* scratch = nullptr;
+    CK(cudaMallocAsync((void**)&scratch, (size_t)3 * D * 8, st));
+    const cudaError_t e = launch_scaler_stats_f64(d_x, N, D, d_fill, d_mean, d_m2, scratch, st);
+    cudaFreeAsync(scratch, st);
+    CK(e);
+    return HLMC_OK;
+}
+
+int hlmc_impute_scale_device(const double* d_x, int64_t N, int64_t D, const int32_t* d_cols, int64_t D_out,
+                             const double* d_fill, const double* d_mean, const double* d_scale, double* d_imputed,
+                             double* d_scaled, int device, void* stream) {
+    if (N < 0 || D < 0 || D_out < 0 || D_out > D) return fail(HLMC_ERR_PARAM, "bad shape");
+    if (N * D_out == 0) return HLMC_OK;
+    if (!d_x || !d_fill || (d_scaled && (!d_mean || !d_scale))) return fail(HLMC_ERR_PARAM, "null argument");
+    CK(cudaSetDevice(device));
+    CK(launch_impute_scale(d_x, N, D, d_cols, D_out, d_fill, d_mean, d_scale, d_imputed, d_scaled,
+                           static_cast<cudaStream_t>(stream)));
     return HLMC_OK;
 }
 

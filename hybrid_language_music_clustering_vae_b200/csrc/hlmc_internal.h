@@ -142,6 +142,31 @@ cudaError_t launch_colstats(const float* x, long long N, long long D, double* me
 cudaError_t launch_standardize(const float* x, float* y, long long N, long long D, const float* mean,
                                const float* scale, cudaStream_t stream);
 cudaError_t measure_fp32_peak(double* tflops);
+
+// librosa.load's front end (hlmc_frontend.cu)
+struct FrontArgs {
+    const void* raw;        // (B, raw_pitch, channels) int16 or float32, interleaved channels
+    int fmt, channels;      // fmt 0: float32, 1: int16
+    long long B, raw_pitch, n_in;
+    float* out;             // (B, pitch) float32
+    long long pitch, n_total, n_out;   // n_out resampled samples, then zeros up to n_total
+    int up, down;           // resample_poly factors after the gcd; 1, 1 = no resampling
+    int n_pre_pad;          // zeros scipy prepends to the filter
+    long long n_pre_remove; // outputs scipy drops at the front
+    int tpp;                // taps per phase
+    const float* hpoly;     // (up, tpp): hpoly[p][t] = h[p + t*up] * up, zero past the filter
+    const long long* valid; // (B) per-clip input frames (<= n_in) or NULL
+};
+cudaError_t launch_frontend(const FrontArgs& a, int num_sms, cudaStream_t stream);
+// tabular normalisation (hlmc_frontend.cu)
+cudaError_t launch_impute_stats(const double* x, long long N, long long D, double* sum, long long* count,
+                                cudaStream_t st);
+cudaError_t launch_scaler_stats_f64(const double* x, long long N, long long D, const double* fill, double* mean,
+                                    double* m2, double* scratch, cudaStream_t st);
+cudaError_t launch_impute_scale(const double* x, long long N, long long D, const int* cols, long long Do,
+                                const double* fill, const double* mean, const double* scale, double* imputed,
+                                double* scaled, cudaStream_t st);
+void count_launch(int n);
 int fast_smem_bytes(const FastTables& ft, int nwarps, int n_fft, int hop, int n_mels);
 int pick_fast_warps(int T);
 long long launch_count();

@@ -28,6 +28,8 @@ namespace hlmc {
 
 static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches += n; }
+constexpr long long kMaxGridY = 65535;
 
 // ---------------------------------------------------------------------------
 // small device helpers
@@ -2413,8 +2415,11 @@ cudaError_t launch_rowmax(const float* in, unsigned int* clipmax, long long B, l
     int gx = (int)((per_clip + 256 * 8 - 1) / (256 * 8));
     if (gx < 1) gx = 1;
     if (gx > 64) gx = 64;
-    rowmax_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(in, clipmax, per_clip);
-    g_launches++;
+    for (long long b0 = 0; b0 < B; b0 += kMaxGridY) {         // gridDim.y is capped at 65535
+        const long long nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+        rowmax_kernel<<<dim3(gx, (unsigned)nb), 256, 0, stream>>>(in + b0 * per_clip, clipmax + b0, per_clip);
+        g_launches++;
+    }
     return cudaGetLastError();
 }
 __global__ void power_to_db_kernel(const float* __restrict__ in, float* __restrict__ out,
@@ -2438,9 +2443,13 @@ cudaError_t launch_power_to_db(const float* in, float* out, const unsigned int* 
     int gx = (int)((per_clip + 256 * 4 - 1) / (256 * 4));
     if (gx < 1) gx = 1;
     if (gx > 256) gx = 256;
-    power_to_db_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(in, out, clipmax, per_clip, ref_mode,
-                                                                  ref_value, amin, top_db);
-    g_launches++;
+    for (long long b0 = 0; b0 < B; b0 += kMaxGridY) {
+        const long long nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+        power_to_db_kernel<<<dim3(gx, (unsigned)nb), 256, 0, stream>>>(in + b0 * per_clip, out + b0 * per_clip,
+                                                                       clipmax + b0, per_clip, ref_mode, ref_value,
+                                                                       amin, top_db);
+        g_launches++;
+    }
     return cudaGetLastError();
 }
 
@@ -2604,8 +2613,12 @@ cudaError_t launch_pcm16_to_f32(const int16_t* raw, long long raw_pitch, float* 
     int gx = (int)((n_total + 256 * 8 - 1) / (256 * 8));
     if (gx < 1) gx = 1;
     if (gx > 128) gx = 128;
-    pcm16_to_f32_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(raw, raw_pitch, out, pitch, n_valid, n_total);
-    g_launches++;
+    for (long long b0 = 0; b0 < B; b0 += kMaxGridY) {
+        const long long nb = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+        pcm16_to_f32_kernel<<<dim3(gx, (unsigned)nb), 256, 0, stream>>>(raw + b0 * raw_pitch, raw_pitch,
+                                                                        out + b0 * pitch, pitch, n_valid, n_total);
+        g_launches++;
+    }
     return cudaGetLastError();
 }
 

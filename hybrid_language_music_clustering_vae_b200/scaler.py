@@ -94,3 +94,81 @@ def fit_transform_device(x, group=None, inplace=False):
                                        C.c_void_p(mean32.data_ptr()), C.c_void_p(scale32.data_ptr()),
                                        x.device.index, C.c_void_p(stream)))
     return y, sc
+
+
+# ---------------------------------------------------------------------------
+# The scripts' tabular normalisation ([R] src/1_preprocessing.py:303-311,
+# src/1_preprocessing_advanced.py:384-391) on device, float64:
+#   np.where(np.isinf(X), np.nan, X) -> SimpleImputer(strategy="mean") -> StandardScaler()
+# ---------------------------------------------------------------------------
+def make_sklearn_imputer(statistics):
+    """A fitted ``SimpleImputer(strategy="mean")`` carrying the given per-column means (NaN = column without
+    any observed value, which sklearn drops on transform)."""
+    from sklearn.impute import SimpleImputer
+
+    im = SimpleImputer(strategy="mean")
+    im.statistics_ = np.asarray(statistics, dtype=np.float64)
+    im.n_features_in_ = int(im.statistics_.shape[0])
+    im._fit_dtype = np.dtype(np.float64)
+    im._fill_dtype = np.dtype(np.float64)
+    im.indicator_ = None
+    return im
+
+
+def fit_transform_tabular_device(x, group=None):
+    """The scripts' inf -> nan, mean-impute, StandardScaler chain for an (N, D) float64 CUDA tensor.
+
+    With ``torch.distributed`` initialised, ``x`` is this rank's rows and the statistics are global
+    (sums / counts add, (mean, m2) combine with Chan's formula).  Returns
+    ``(imputed (N, D'), scaled (N, D'), sklearn SimpleImputer, sklearn StandardScaler)`` where D' drops the
+    columns without a single finite value, as sklearn does."""
+    import torch
+
+    assert x.is_cuda and x.dtype == torch.float64 and x.dim() == 2
+    x = x.contiguous()
+    N, D = x.shape
+    dev = x.device
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    csum = torch.empty((D,), dtype=torch.float64, device=dev)
+    ccnt = torch.empty((D,), dtype=torch.int64, device=dev)
+    _check(lib.hlmc_impute_stats_device(ptr(x), N, D, ptr(csum), ptr(ccnt), dev.index, stream))
+    dist = None
+    try:
+        import torch.distributed as tdist
+
+        if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
+            dist = tdist
+    except ImportError:  # pragma: no cover
+        pass
+    n_total = float(N)
+    if dist is not None:
+        dist.all_reduce(csum, group=group)
+        dist.all_reduce(ccnt, group=group)
+    fill = csum / ccnt.to(torch.float64)                 # NaN where a column has no finite entry
+    keep = torch.nonzero(ccnt > 0).flatten().to(torch.int32)
+    Do = int(keep.numel())
+    imputer = make_sklearn_imputer(fill.cpu().numpy())
+    fill_safe = torch.nan_to_num(fill, nan=0.0)
+    mean = torch.empty((D,), dtype=torch.float64, device=dev)
+    m2 = torch.empty((D,), dtype=torch.float64, device=dev)
+    _check(lib.hlmc_scaler_stats_f64_device(ptr(x), N, D, ptr(fill_safe), ptr(mean), ptr(m2), dev.index, stream))
+    if dist is not None:
+        cnt = torch.tensor([float(N)], dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt, group=group)
+        s1 = mean * float(N)
+        dist.all_reduce(s1, group=group)
+        gmean = s1 / cnt
+        m2 = m2 + float(N) * (mean - gmean) ** 2
+        dist.all_reduce(m2, group=group)
+        mean, n_total = gmean, float(cnt.item())
+    keep64 = keep.to(torch.int64)
+    mean_k, var_k = mean[keep64], (m2 / max(n_total, 1.0))[keep64]
+    scaler = make_sklearn_scaler(n_total, mean_k.cpu().numpy(), var_k.cpu().numpy())
+    mean_d = torch.from_numpy(scaler.mean_).to(dev)
+    scale_d = torch.from_numpy(scaler.scale_).to(dev)
+    imputed = torch.empty((N, Do), dtype=torch.float64, device=dev)
+    scaled = torch.empty((N, Do), dtype=torch.float64, device=dev)
+    _check(lib.hlmc_impute_scale_device(ptr(x), N, D, ptr(keep), Do, ptr(fill_safe), ptr(mean_d), ptr(scale_d),
+                                        ptr(imputed), ptr(scaled), dev.index, stream))
+    return imputed, scaled, imputer, scaler

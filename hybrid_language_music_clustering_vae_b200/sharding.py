@@ -101,33 +101,58 @@ def gather_host(local: np.ndarray, B: int, rank: int, world: int, group=None, ds
 
 def extract_multi_gpu(waves: np.ndarray, devices, extractor_kwargs: dict, **extract_kw):
     """Single-process variant: one host thread and one plan per device, outputs written
-    into slices of shared host arrays (the "host gather")."""
+    into slices of shared host arrays (the "host gather").
+
+    Every keyword of ``FeatureExtractor.extract_host`` is honoured (``pad_to``, ``pooled``, ``chroma``,
+    ``fixed_frames``, ``sr_in``, ...): the shared arrays are sized from them, and each rank writes
+    straight into its slice (``extract_host`` refuses a buffer of the wrong shape instead of
+    replacing it, so nothing can land in a private array)."""
+    from ._lib import lib
     from .core import FeatureExtractor
 
+    waves = np.asarray(waves)
     B = waves.shape[0]
     world = len(devices)
     exs = [FeatureExtractor(device=d, **extractor_kwargs) for d in devices]
-    T = exs[0].num_frames(waves.shape[1])
-    want = dict(logmel=True, mfcc=True, stats=True, status=True, pooled=False)
-    want.update({k: v for k, v in extract_kw.items() if k in want})
+    ex0 = exs[0]
+    kw = dict(extract_kw)
+    kw.pop("out", None)
+    sr_in = int(kw.get("sr_in") or 0)
+    if sr_in == ex0.params.sr:
+        sr_in = 0
+    n_res = int(lib.hlmc_resampled_length(waves.shape[1], sr_in, ex0.params.sr)) if sr_in else waves.shape[1]
+    n_total = int(kw.get("pad_to") or n_res)
+    T = ex0.num_frames(n_total)
+    chroma = kw.get("chroma", False)
+    has_mfcc = ex0.n_mfcc > 0
     out = {}
-    if want["logmel"]:
-        out["logmel"] = np.empty((B, exs[0].n_mels, T), np.float32)
-    if want["mfcc"] and exs[0].n_mfcc > 0:
-        out["mfcc"] = np.empty((B, exs[0].n_mfcc, T), np.float32)
-    if want["stats"]:
+    if kw.get("logmel", True):
+        out["logmel"] = np.empty((B, ex0.n_mels, T), np.float32)
+    if kw.get("mfcc", True) and has_mfcc:
+        out["mfcc"] = np.empty((B, ex0.n_mfcc, T), np.float32)
+    if kw.get("stats", True):
         out["stats"] = np.empty((B, 5, T), np.float32)
-    if want["status"]:
+    if kw.get("status", True):
         out["status"] = np.empty((B,), np.int32)
-    if want["pooled"]:
-        out["pooled"] = np.empty((B, exs[0].pooled_width(exs[0].n_mfcc > 0)), np.float32)
+    if kw.get("pooled", False):
+        out["pooled"] = np.empty((B, ex0.pooled_width(has_mfcc, bool(chroma))), np.float32)
+    if chroma and chroma != "pooled":
+        out["chroma"] = np.empty((B, 12, T), np.float32)
+        out["tuning"] = np.empty((B,), np.float32)
+    if kw.get("fixed_frames"):
+        out["fixed_logmel"] = np.empty((B, ex0.n_mels, int(kw["fixed_frames"])), np.float32)
+    if kw.get("wave_out"):
+        out["wave"] = np.empty((B, n_total), np.float32)
     errs = []
 
     def work(r):
         try:
             lo, hi = shard_bounds(B, r, world)
             if hi > lo:
-                exs[r].extract_host(waves[lo:hi], out={k: v[lo:hi] for k, v in out.items()}, **extract_kw)
+                mine = {k: v[lo:hi] for k, v in out.items()}
+                got = exs[r].extract_host(waves[lo:hi], out=mine, **kw)
+                for k, v in mine.items():
+                    assert got[k] is v, f"rank {r}: output {k!r} did not land in the shared array"
         except Exception as e:  # surfaced after join
             errs.append(e)
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define HLMC_ABI_VERSION 1
+#define HLMC_ABI_VERSION 2
 
 typedef enum hlmc_status {
     HLMC_OK = 0,
@@ -240,13 +240,29 @@ int hlmc_extract_host_ex(hlmc_plan *plan, const void *h_wave, int sample_format,
                          float *h_mfcc, float *h_stats, int32_t *h_status, float *h_pooled,
                          int64_t chunk_clips, int n_streams);
 
-/* The general host entry point: everything above plus chroma_stft, as one POD request.
- * Any output pointer may be NULL.  pooled_with_chroma != 0 appends [chroma mean | chroma std]
- * to the pooled rows (the scripts' full 370 / 290 columns).                              */
+/* The general host entry point: everything above plus chroma_stft, the advanced script's fixed-width
+ * image and the rest of librosa.load's front end, as one POD request (zero-initialise it: a zero field
+ * means "not wanted" / "default").  Any output pointer may be NULL.  pooled_with_chroma != 0 appends
+ * [chroma mean | chroma std] to the pooled rows (the scripts' full 370 / 290 columns).
+ *
+ * Front end ([R] src/1_preprocessing.py:137-153, src/1_preprocessing_advanced.py:79-94,
+ * librosa.load(path, sr=22050, duration=30) then np.pad to sr * duration):
+ *   channels > 1 : `wave` holds interleaved frames (as in the WAV data chunk); the device averages the
+ *                  channels in float32 in channel order, then divides by the count (librosa.to_mono = np.mean)
+ *   sr_in != 0 and != params.sr : the mono signal is resampled sr_in -> params.sr on the device with
+ *                  librosa.resample(res_type="polyphase") = scipy.signal.resample_poly(up, down) with its
+ *                  default Kaiser(beta=5) low-pass of 20*max(up,down)+1 taps, output length
+ *                  ceil(n_valid * sr / sr_in) (librosa's fix_length).  librosa.load's DEFAULT res_type is
+ *                  "soxr_hq", a different (also linear-phase, higher-order) low-pass: results differ in the
+ *                  transition band above ~0.45 sr; pass res_type="polyphase" on the reference side for parity.
+ *   n_valid, pitch : in FRAMES of the input (one frame = `channels` samples); n_total: samples per clip
+ *                  AFTER resampling that the features see (right zero pad, the scripts' np.pad).
+ * fixed_logmel ([R] src/1_preprocessing_advanced.py:108-112): the log-mel image cropped to
+ * fixed_frames frames or right-padded with the clip's minimum, (B, n_mels, fixed_frames).        */
 typedef struct hlmc_host_io {
-    const void *wave;          /* (B, pitch) float32 or int16                             */
+    const void *wave;          /* (B, pitch [, channels]) float32 or int16                */
     int32_t     sample_format; /* HLMC_SAMPLES_*                                          */
-    int64_t     B, n_valid, pitch, n_total;   /* n_total <= 0 means n_valid               */
+    int64_t     B, n_valid, pitch, n_total;   /* n_total <= 0 means the (resampled) clip length */
     float      *logmel;        /* (B, n_mels, T)                                          */
     float      *mfcc;          /* (B, n_mfcc, T)                                          */
     float      *stats;         /* (B, 5, T)                                               */
@@ -257,6 +273,17 @@ typedef struct hlmc_host_io {
     int32_t     pooled_with_chroma;
     int64_t     chunk_clips;   /* <= 0: chosen by the library                             */
     int32_t     n_streams;     /* <= 0: 3                                                 */
+    /* ABI 2 */
+    int32_t     channels;      /* <= 1: mono                                              */
+    int32_t     sr_in;         /* 0: already at params.sr                                 */
+    int32_t     reserved0;
+    float      *fixed_logmel;  /* (B, n_mels, fixed_frames) or NULL                       */
+    int64_t     fixed_frames;
+    float      *wave_out;      /* (B, n_total) float32: the clips as the features saw them (after mono mix,
+                                  resampling and padding), or NULL                        */
+    const int64_t *valid_frames; /* (B) per-clip frame counts <= n_valid, or NULL (all n_valid): files shorter
+                                  than `duration` -- frames past a clip's count are ignored, its resampled
+                                  length follows its own count, the rest of n_total is the zero pad  */
 } hlmc_host_io;
 int hlmc_extract_host_io(hlmc_plan *plan, const hlmc_host_io *io);
 
@@ -274,6 +301,39 @@ int hlmc_column_stats_device(const float *d_x, int64_t N, int64_t D, double *d_m
                              int device, void *stream);
 int hlmc_standardize_device(const float *d_x, float *d_y, int64_t N, int64_t D,
                             const float *d_mean, const float *d_scale, int device, void *stream);
+
+/* librosa.load's front end for a device-resident batch (see hlmc_host_io for the semantics):
+ * int16 / float32, interleaved channels -> mono float32 -> polyphase resampling -> right zero pad.
+ *   d_raw   : (B, raw_pitch, channels) samples, raw_pitch in frames
+ *   d_wave  : (B, pitch) float32 out, n_total samples written per clip
+ * hlmc_resampled_length = ceil(n_in * sr_out / sr_in), librosa.resample's output length.            */
+int64_t hlmc_resampled_length(int64_t n_in, int32_t sr_in, int32_t sr_out);
+int hlmc_load_frontend_device(hlmc_plan *plan, const void *d_raw, int sample_format, int channels,
+                              int64_t B, int64_t n_in, int64_t raw_pitch, int32_t sr_in,
+                              float *d_wave, int64_t pitch, int64_t n_total,
+                              const int64_t *d_valid_frames /* (B) or NULL */, void *stream);
+/* The taps the resampler uses (scipy.signal.firwin(20*max(up,down)+1, 1/max(up,down), window=("kaiser", 5.0))
+ * cast to float32, times up): fills up to `cap` floats, returns the tap count (or < 0).              */
+int64_t hlmc_resample_taps(int32_t sr_in, int32_t sr_out, float *h_out, int64_t cap);
+
+/* The scripts' tabular normalisation on device ([R] src/1_preprocessing.py:303-311,
+ * src/1_preprocessing_advanced.py:384-391) for the (N, 370) / (N, 290) float64 feature matrix:
+ *   np.where(np.isinf(X), np.nan, X) -> SimpleImputer(strategy="mean") -> StandardScaler().
+ * hlmc_impute_stats_device : per column, the sum and the count of the finite entries
+ *     (SimpleImputer.statistics_ = sum / count; a column with count 0 is dropped by sklearn);
+ * hlmc_scaler_stats_f64_device : per column of the imputed matrix (non-finite -> d_fill[c]) the mean and the
+ *     corrected sum of squared deviations (var = m2 / N), as sklearn's _incremental_mean_and_var;
+ * hlmc_impute_scale_device : d_imputed[r, j] = x[r, cols[j]] or d_fill[cols[j]] where non-finite;
+ *     d_scaled[r, j] = (d_imputed[r, j] - mean[j]) / scale[j].  cols (D_out int32) lists the kept
+ *     columns; either output may be NULL.  Per-rank sums / counts / (mean, m2) combine across GPUs by
+ *     addition / Chan's formula on the caller's side (torch.distributed), the only collectives of the path. */
+int hlmc_impute_stats_device(const double *d_x, int64_t N, int64_t D, double *d_sum, int64_t *d_count,
+                             int device, void *stream);
+int hlmc_scaler_stats_f64_device(const double *d_x, int64_t N, int64_t D, const double *d_fill,
+                                 double *d_mean, double *d_m2, int device, void *stream);
+int hlmc_impute_scale_device(const double *d_x, int64_t N, int64_t D, const int32_t *d_cols, int64_t D_out,
+                             const double *d_fill, const double *d_mean, const double *d_scale,
+                             double *d_imputed, double *d_scaled, int device, void *stream);
 
 /* Measurement helper: a dependent-FMA micro-benchmark that returns the
  * achieved FP32 TFLOP/s of the plan's device (the FP32-pipe roofline

@@ -633,3 +633,80 @@ def extract_flattened_features(audio, sr, cfg=ADV_CONFIG, with_chroma=True):
         features.extend(np.mean(chroma, axis=1))
         features.extend(np.std(chroma, axis=1))
     return np.array(features)
+
+
+# --------------------------------------------------------------------------
+# librosa.load's arithmetic (the scripts' load_audio_file, [R] src/1_preprocessing.py:137-153,
+# src/1_preprocessing_advanced.py:79-94), restated for PCM16 frames that the caller has already read [L]:
+#   soundfile read(dtype=float32): int16 / 32768            -> pcm16_to_float
+#   librosa.to_mono: np.mean over the channel axis           -> to_mono
+#   librosa.resample(res_type="polyphase"): scipy.signal.resample_poly(y, sr/gcd, orig/gcd) followed by
+#     util.fix_length(size=ceil(n * ratio))                  -> resample
+# librosa.load's DEFAULT res_type is "soxr_hq" (the soxr library, not installed here and a different
+# low-pass): the device front end implements the "polyphase" type, which IS scipy's resample_poly, so
+# this part of the oracle is pinned by a third-party implementation.
+# --------------------------------------------------------------------------
+def pcm16_to_float(frames):
+    return (np.asarray(frames, dtype=np.int16).astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+
+
+def to_mono(y):
+    """y: (channels, n) as soundfile hands it to librosa (after the transpose)."""
+    if y.ndim > 1:
+        y = np.mean(y, axis=tuple(range(y.ndim - 1)))
+    return y
+
+
+def fix_length(data, *, size, axis=-1):
+    n = data.shape[axis]
+    if n > size:
+        slices = [slice(None)] * data.ndim
+        slices[axis] = slice(0, size)
+        return data[tuple(slices)]
+    if n < size:
+        lengths = [(0, 0)] * data.ndim
+        lengths[axis] = (0, size - n)
+        return np.pad(data, lengths, mode="constant")
+    return data
+
+
+def resample(y, *, orig_sr, target_sr, res_type="polyphase", fix=True):
+    if orig_sr == target_sr:
+        return y
+    if res_type != "polyphase":
+        raise ParameterError("the oracle restates res_type='polyphase' only (soxr is not installed)")
+    ratio = float(target_sr) / orig_sr
+    n_samples = int(np.ceil(y.shape[-1] * ratio))
+    g = np.gcd(int(orig_sr), int(target_sr))
+    y_hat = scipy.signal.resample_poly(y, int(target_sr) // g, int(orig_sr) // g, axis=-1)
+    if fix:
+        y_hat = fix_length(y_hat, size=n_samples)
+    return np.asarray(y_hat, dtype=y.dtype)
+
+
+def load_pcm16(frames, sr_native, *, sr=22050, mono=True, duration=None, res_type="polyphase"):
+    """librosa.load for PCM16 frames (n, channels) already read from the container -> (y float32, sr)."""
+    frames = np.asarray(frames)
+    if frames.ndim == 1:
+        frames = frames[:, None]
+    if duration is not None:
+        frames = frames[: int(duration * sr_native)]
+    y = pcm16_to_float(frames).T                     # (channels, n)
+    if mono:
+        y = to_mono(y)
+    elif y.shape[0] == 1:
+        y = y[0]
+    if sr is not None and sr != sr_native:
+        y = resample(y, orig_sr=sr_native, target_sr=sr, res_type=res_type)
+    else:
+        sr = sr_native
+    return np.asarray(y, dtype=np.float32), sr
+
+
+def load_audio_file_pcm16(frames, sr_native, cfg=BASIC_CONFIG):
+    """[R] src/1_preprocessing.py:137-153 after the container is read: load + right zero pad."""
+    audio, sr = load_pcm16(frames, sr_native, sr=cfg["sample_rate"], duration=cfg["duration"])
+    expected = cfg["sample_rate"] * cfg["duration"]
+    if len(audio) < expected:
+        audio = np.pad(audio, (0, expected - len(audio)), mode="constant")
+    return audio, sr

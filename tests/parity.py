@@ -71,9 +71,17 @@ def fp32_floor_allowance(S, sr, n_fft):
     return d_cen, d_bw
 
 
-def compare_clip(got: dict, want: dict, *, sr=22050, n_fft=2048, roll_percent=0.85):
-    """Returns a dict of error metrics; raises nothing."""
-    m = {}
+def is_degenerate(y) -> bool:
+    """Clips whose spectrum is a single line or empty: constant (zero / DC), a single non-zero sample, or
+    n <= 2.  Only for these may centroid / bandwidth use the float32-FFT floor allowance."""
+    y = np.asarray(y)
+    return bool(y.size <= 2 or np.ptp(y) == 0 or np.count_nonzero(y) <= 1)
+
+
+def compare_clip(got: dict, want: dict, *, sr=22050, n_fft=2048, roll_percent=0.85, y=None):
+    """Returns a dict of error metrics; raises nothing.  Pass the clip `y` so that the floor allowance is
+    confined to degenerate clips; without it the raw errors are asserted."""
+    m = {"degenerate": bool(y is not None and is_degenerate(y))}
     m["frames_equal"] = got["logmel"].shape == want["logmel"].shape
     m["logmel_maxabs_db"] = float(np.abs(got["logmel"] - want["logmel"]).max())
     if "mfcc" in got and "mfcc" in want:
@@ -102,7 +110,12 @@ def assert_clip(m: dict, where=""):
     assert m["logmel_maxabs_db"] <= LOGMEL_TOL_DB, f"log-mel {m['logmel_maxabs_db']} dB {where}"
     if "mfcc_rel" in m:
         assert m["mfcc_rel"] <= REL_TOL, f"mfcc {m['mfcc_rel']} {where}"
-    for k in ("centroid_rel", "bandwidth_rel", "zcr_rel", "rms_rel"):
+    for k in ("centroid", "bandwidth"):
+        # raw error for every ordinary clip; the float32-floor allowance only for single-line spectra
+        key = k + ("_rel" if m.get("degenerate") else "_raw_rel")
+        if key in m:
+            assert m[key] <= REL_TOL, f"{key} {m[key]} {where}"
+    for k in ("zcr_rel", "rms_rel"):
         if k in m:
             assert m[k] <= REL_TOL, f"{k} {m[k]} {where}"
     if "rolloff_unexplained" in m:

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(built):
     for n in names:
         assert hasattr(_lib.lib, n), f"{n} is declared in include/hlmc_b200.h but not exported"
     assert set(_lib.EXPORTS) == set(names)
-    assert _lib.lib.hlmc_abi_version() == 1
+    assert _lib.lib.hlmc_abi_version() == 2 == _lib.ABI_VERSION
 
 
 def test_params_struct_matches_header(built):
@@ -41,6 +41,30 @@ def test_params_struct_matches_header(built):
     lib.hlmc_params_default(C.byref(p))
     assert (p.sr, p.n_fft, p.hop_length, p.n_mels, p.n_mfcc) == (22050, 2048, 512, 128, 20)
     assert p.pad_mode == 0 and p.center == 1 and abs(p.top_db - 80.0) < 1e-6 and abs(p.amin - 1e-10) < 1e-16
+
+
+def test_host_io_struct_matches_header(built):
+    """Field order and types of hlmc_host_io (ABI 2) as the ctypes mirror declares them."""
+    from hybrid_language_music_clustering_vae_b200._lib import HlmcHostIo
+
+    src = open(os.path.join(ROOT, "include", "hlmc_b200.h")).read()
+    body = src[src.index("typedef struct hlmc_host_io {"):src.index("} hlmc_host_io;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in re.findall(r"^\s*(?:const\s+)?(?:void|float|int32_t|int64_t)\s*\**\s*([\w\s,\*]+);", body, flags=re.M):
+        names += [n.strip().lstrip("*") for n in decl.split(",")]
+    assert names == [f for f, _t in HlmcHostIo._fields_]
+    assert C.sizeof(HlmcHostIo) % 8 == 0
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """bench.py --impl reference must not import the package (the arm's record listed libhlmc_b200.so)."""
+    code = ("import sys, runpy; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0','--cpu-sample','8'];"
+            "runpy.run_path(%r, run_name='__main__');"
+            "assert not any('hybrid_language_music_clustering_vae_b200' == m.split('.')[0] for m in sys.modules), 'package imported';"
+            "assert 'libhlmc_b200' not in open('/proc/self/maps').read(), 'library mapped'; print('CLEAN')" % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "CLEAN" in out.stdout, out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("n,T", [(66150, 130), (661500, 1292), (2047, 4), (2048, 5), (2049, 5), (511, 1)])
@@ -176,6 +200,16 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config"):
         assert k in line
+    st = line["cpu_baseline"]["single_thread"]
+    assert st["cores"] == 1 and st["value"] > 0
+    # both arms build `config` with the same function, so the driver's same_config check can hold
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import argparse
+    args = argparse.Namespace(clips=10000, seconds=3.0, chroma=False)
+    assert line["config"] == bench.make_config(args, 1)
 
 
 def test_chan_combination_of_shard_statistics(built):

@@ -38,7 +38,7 @@ def _check_batch(hl, y, generic=False, pitch=None, **kw):
     for i in range(y.shape[0]):
         want = oracle_clip(y[i], **okw)
         got = {k: res[k][i] for k in ("logmel", "mfcc", "stats") if k in res}
-        m = compare_clip(got, want, n_fft=kw.get("n_fft", 2048), roll_percent=kw.get("roll_percent", 0.85))
+        m = compare_clip(got, want, n_fft=kw.get("n_fft", 2048), roll_percent=kw.get("roll_percent", 0.85), y=y[i])
         assert_clip(m, where=f"clip {i} {kw} generic={generic}")
         flips += m.get("rolloff_flips", 0)
     frames = y.shape[0] * res["logmel"].shape[-1]
@@ -383,7 +383,8 @@ def test_chroma_stft_and_tuning_on_device(built):
                 res[res >= 0.5] -= 1.0
                 counts, edges = np.histogram(res, np.linspace(-0.5, 0.5, 101))
                 got = int(round((tu[i] + 0.5) * 100))
-                assert counts[got] >= counts.max() - 2, f"tuning {tu[i]} vs {t_or} without a near tie (clip {i})"
+                assert counts[got] == counts.max(), (f"tuning {tu[i]} vs {t_or}: the device's bin holds {counts[got]} "
+                                                     f"candidates, the oracle's arg-max {counts.max()} (clip {i})")
                 ties += 1
             want = orc.chroma_stft(y=y[i], sr=SR, tuning=float(tu[i]))
             assert ch[i].shape == want.shape == (12, 1 + n // 512)
