@@ -261,14 +261,16 @@ def reference_arm(args, rank, world):
     synth = load_synth()
     n = int(round(args.seconds * SR))
     cores = host_cores()
-    pilot = synth.synth_batch(max(64, 8 * cores), n, seed=20261, mixture=False)
+    pilot = synth.synth_batch(max(128, 32 * cores), n, seed=20261, mixture=False)
     arm = CpuArm(pilot, cores)
     rate = len(pilot) / arm.run()
     arm.close()
-    # bounded sample, but long steps: >= 4,000 clips per step whenever the whole run fits ~3 minutes, so that
-    # pool dispatch and the straggler tail are < 2 % of a step
-    budget_s = 170.0
-    per_step = args.cpu_sample or int(max(8 * cores, min(args.clips, rate * budget_s / (args.steps + 1))))
+    # bounded sample, but long steps: >= 4,000 clips per step (pool dispatch and the straggler tail are then
+    # < 2 % of a step) unless that would push the whole run past ~6 minutes
+    per_step = int(min(args.clips, max(4000, rate * 170.0 / (args.steps + 1))))
+    if per_step * (args.steps + 1) / rate > 360.0:
+        per_step = int(max(8 * cores, rate * 360.0 / (args.steps + 1)))
+    per_step = args.cpu_sample or per_step
     clips = synth.synth_batch(per_step, n, seed=20261, mixture=False)
     st_rate, st_n = single_thread_rate(clips)
     arm = CpuArm(clips, cores)
@@ -590,10 +592,11 @@ def main():
             os.environ.setdefault(k, "1")
         cores = host_cores()
         hw = h_wave_t.numpy()
-        arm = CpuArm(hw[: min(B, max(64, 8 * cores))], cores)
+        arm = CpuArm(hw[: min(B, max(128, 32 * cores))], cores)
         rate = arm.n / arm.run()
         arm.close()
-        ns = args.cpu_sample or int(max(8 * cores, min(B, rate * 15.0)))      # ~15 s of CPU work, one long step
+        # one long step: >= 4,000 clips (what the reference arm uses per step), ~15-30 s of CPU work
+        ns = args.cpu_sample or int(min(B, max(4000, rate * 15.0)))
         arm = CpuArm(hw[:ns], cores)
         t = arm.run()
         arm.close()
