@@ -121,8 +121,12 @@ class _Feature:
         yb, lead, on_dev = _prep(y)
         ex = get_extractor(**kw, device=_device_of(yb, on_dev))
         if on_dev:
+            # device input: asynchronous, no host synchronisation - non-finite audio is NOT raised here (that
+            # would need a device-to-host read); use FeatureExtractor.extract_device and inspect ``status``
             res = ex.extract_device(yb, mfcc=(want == "mfcc"), stats=(want == "stats"))
         else:
+            if not np.isfinite(yb).all():          # librosa.util.valid_audio: the whole buffer, not only framed samples
+                raise ParameterError("Audio buffer is not finite everywhere")
             res = ex.extract_host(yb, logmel=(want in ("logmel",)), mfcc=(want == "mfcc"),
                                   stats=(want == "stats"))
             _valid_or_raise(res["status"])

@@ -54,6 +54,11 @@ enum { HLMC_STAT_CENTROID = 0, HLMC_STAT_BANDWIDTH = 1, HLMC_STAT_ROLLOFF = 2,
 /* per-clip status bits (the batched analogue of the scripts' per-file
  * try/except: [R] src/1_preprocessing.py:238-251, _advanced.py:165-183)      */
 enum { HLMC_CLIP_NONFINITE = 1 };
+/* Coverage of HLMC_CLIP_NONFINITE: a clip is flagged when a frame's sum of squares is not finite, i.e. when a
+ * non-finite sample lies inside some analysis frame.  librosa.util.valid_audio checks the whole buffer; samples
+ * that no frame covers (center=False tails, hop_length > n_fft) are therefore not checked here.  The numpy
+ * entry points of the Python layer run np.isfinite over the whole clip first and raise ParameterError as
+ * librosa does; CUDA-tensor entry points return the status array and leave the decision to the caller.   */
 
 /* One POD block holding every keyword the reference passes (or leaves at its
  * librosa default) at the call sites of SURVEY.md section 8(a).              */
@@ -149,7 +154,9 @@ int hlmc_graph_launch(hlmc_graph *graph, void *stream);
 void hlmc_graph_destroy(hlmc_graph *graph);
 
 /* The same plus librosa.feature.chroma_stft ([R] src/1_preprocessing.py:96-101,
- * src/1_preprocessing_advanced.py:139-141; n_fft = 2048, power = 2 plans only):
+ * src/1_preprocessing_advanced.py:139-141).  SCOPE: plans with n_fft = 2048 and power = 2 only - the one
+ * configuration both scripts use; any other n_fft returns HLMC_ERR_UNSUPPORTED (chroma for n_fft 512 / 1024 /
+ * 4096 is OUT of this library: the piptrack epilogue and the power-spectrum stash live in the 2048 kernel):
  *   d_chroma : (B, 12, T) float32, each frame divided by its largest chroma bin, or NULL
  *   d_tuning : (B) float32, the per-clip librosa.estimate_tuning result, or NULL
  *   d_work   : hlmc_chroma_workspace_bytes(plan, B, n) bytes of device scratch

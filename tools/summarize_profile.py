@@ -48,6 +48,13 @@ for r in rows[2:]:
 with open(os.path.join(out_dir, f"{tag}_ncu_summary.json"), "w") as f:
     json.dump(summary, f, indent=1)
 
+sys.path.insert(0, ROOT)
+import importlib.util
+_spec = importlib.util.spec_from_file_location("bench_for_hash", os.path.join(ROOT, "bench.py"))
+_bench = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_bench)
+SOURCE_HASH = _bench.kernel_source_hash()      # bench.py quotes a capture only when this matches the built sources
+
 def unit_scale(u):
     return {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 
@@ -57,10 +64,11 @@ for k in summary:
         wr = k["dram__bytes_write.sum"] * unit_scale(k["dram__bytes_write.sum__unit"])
         with open(os.path.join(out_dir, "frames_fast_traffic.json"), "w") as f:
             json.dump({"source": f"profiles/{tag}_ncu_summary.json (ncu --set full, one launch)",
-                       "clips_in_capture": clips, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                       "source_hash": SOURCE_HASH, "clips_in_capture": clips, "dram_bytes_read": rd, "dram_bytes_write": wr,
                        "dram_bytes_per_launch": rd + wr, "dram_bytes_per_clip": (rd + wr) / clips}, f, indent=1)
         with open(os.path.join(out_dir, "frames_fast_pipes.json"), "w") as f:
             json.dump({"source": f"profiles/{tag}_ncu_summary.json (ncu --set full, one launch, {clips} clips)",
+                       "source_hash": SOURCE_HASH,
                        "fp32_pipe_cycles_active_pct": k.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                        "fma_pipe_pct": k.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
                        "alu_pipe_pct": k.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
