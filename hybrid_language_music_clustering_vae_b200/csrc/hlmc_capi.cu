@@ -275,6 +275,7 @@ static int ensure_chroma_tables(hlmc_plan* pl) {
     if (pl->p.n_fft != kFastNfft || !pl->fast_ok)
         return fail(HLMC_ERR_UNSUPPORTED, "chroma_stft on device needs n_fft = 2048 (the register-FFT kernel)");
     if (pl->p.power != 2.0f) return fail(HLMC_ERR_UNSUPPORTED, "chroma_stft on device needs a power=2 plan");
+    CK(cudaSetDevice(pl->device));       // callers may be on a fresh host thread whose current device is 0
     const int F = pl->F;
     // bins np.linspace(-0.5, 0.5, 101) of librosa.pitch_tuning (resolution 0.01)
     std::vector<double> edges(kTuningBins + 1);
@@ -1162,6 +1163,7 @@ static int get_resampler(hlmc_plan* pl, int sr_in, const ResampleTaps** out) {
     ResampleTaps r;
     build_resample_filter(sr_in, pl->p.sr, r);
     if ((int64_t)r.up * r.tpp > (int64_t(1) << 24)) return fail(HLMC_ERR_UNSUPPORTED, "resampling ratio too fine");
+    CK(cudaSetDevice(pl->device));
     std::vector<float> poly((size_t)r.up * r.tpp, 0.0f);
     for (int p = 0; p < r.up; ++p)
         for (int t = 0; t < r.tpp; ++t) {
