@@ -216,13 +216,13 @@ class ClockSampler:
 
 
 def kernel_source_hash():
-    """sha256 over the CUDA sources: an ncu capture is only quoted when it was taken from these exact files."""
+    """sha256 over the sources of the captured kernels (hlmc_kernels.cu and the headers it includes): an ncu
+    capture is only quoted when it was taken from these exact files."""
     h = hashlib.sha256()
     csrc = os.path.join(PKG, "csrc")
-    for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh", ".h")):
-            with open(os.path.join(csrc, name), "rb") as f:
-                h.update(name.encode() + b"\0" + f.read())
+    for name in ("fft_inreg.cuh", "fft_inreg2.cuh", "hlmc_internal.h", "hlmc_kernels.cu"):
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
 
 
