@@ -108,12 +108,22 @@ def extract_multi_gpu(waves: np.ndarray, devices, extractor_kwargs: dict, **extr
     straight into its slice (``extract_host`` refuses a buffer of the wrong shape instead of
     replacing it, so nothing can land in a private array)."""
     from ._lib import lib
-    from .core import FeatureExtractor
+    from .core import FeatureExtractor, get_extractor
 
     waves = np.asarray(waves)
     B = waves.shape[0]
     world = len(devices)
-    exs = [FeatureExtractor(device=d, **extractor_kwargs) for d in devices]
+    # one plan per DISTINCT device from the process-wide cache (plans keep their pinned-pipeline slots and lazily
+    # built tables between calls); a device listed twice gets a private second plan, since a plan serves one
+    # host thread at a time
+    seen, exs, private = set(), [], []
+    for d in devices:
+        if d in seen:
+            exs.append(FeatureExtractor(device=d, **extractor_kwargs))
+            private.append(exs[-1])
+        else:
+            seen.add(d)
+            exs.append(get_extractor(device=d, **extractor_kwargs))
     ex0 = exs[0]
     kw = dict(extract_kw)
     kw.pop("out", None)
@@ -159,7 +169,7 @@ def extract_multi_gpu(waves: np.ndarray, devices, extractor_kwargs: dict, **extr
     th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
     [t.start() for t in th]
     [t.join() for t in th]
-    for ex in exs:
+    for ex in private:
         ex.close()
     if errs:
         raise errs[0]
