@@ -9,8 +9,8 @@ batched entry that replaces their per-file loops.
 from .core import (FeatureExtractor, ParameterError, UnsupportedError, STAT_NAMES, get_extractor,
                    launch_count, measure_fp32_peak)
 from .api import stft, power_to_db, feature
-from . import preprocessing, scaler, sharding, synth
+from . import pipeline, preprocessing, scaler, sharding, synth
 
 __all__ = ["FeatureExtractor", "ParameterError", "UnsupportedError", "STAT_NAMES", "get_extractor",
            "launch_count", "measure_fp32_peak", "stft", "power_to_db", "feature", "preprocessing",
-           "scaler", "sharding", "synth"]
+           "scaler", "sharding", "synth", "pipeline"]

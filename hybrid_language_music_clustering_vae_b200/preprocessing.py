@@ -223,32 +223,73 @@ def load_audio_file(file_path, cfg=BASIC_CONFIG, device=0):
         return None, None
 
 
-def process_files_advanced(file_infos, cfg=ADV_CONFIG, chroma="device", device=0):
-    """The advanced script's ``Parallel(...)(delayed(process_single_file)(f) ...)`` map ([R] _advanced.py:286-288)
-    as batched device calls: files are decoded on the host, grouped by (rate, channels) and run through the
-    host pipeline with per-clip lengths.  Returns the list of per-file dicts ``process_single_file`` returns."""
-    results = [None] * len(file_infos)
-    groups = {}
+def _decode_groups(file_infos, cfg):
+    """Parse the containers and group the clips by (native rate, channels).  -> (groups, load_failed indices)"""
+    groups, failed = {}, []
     for i, info in enumerate(file_infos):
         try:
             frames, sr_native = read_wav_pcm16(info["path"], cfg["duration"])
             if len(frames) == 0:
                 raise ValueError("empty file")
             groups.setdefault((sr_native, frames.shape[1]), []).append((i, frames))
-        except Exception:
-            results[i] = {"status": "failed", "path": info["path"], "error": "Load failed"}
+        except Exception as e:
+            print(f"Error loading {info['path']}: {e}")
+            failed.append(i)
+    return groups, failed
+
+
+def _stack_group(items, sr_native, cfg):
+    n_max = max(len(f) for _i, f in items)
+    raw = np.zeros((len(items), n_max, items[0][1].shape[1]), np.int16)
+    valid = np.empty((len(items),), np.int64)
+    for k, (_i, f) in enumerate(items):
+        raw[k, :len(f)] = f
+        valid[k] = len(f)
     expected = cfg["sample_rate"] * cfg["duration"]
-    for (sr_native, ch), items in groups.items():
-        n_max = max(len(f) for _i, f in items)
-        raw = np.zeros((len(items), n_max, ch), np.int16)
-        valid = np.empty((len(items),), np.int64)
-        for k, (_i, f) in enumerate(items):
-            raw[k, :len(f)] = f
-            valid[k] = len(f)
-        n_res = int(np.ceil(n_max * cfg["sample_rate"] / sr_native))
+    n_res = int(np.ceil(n_max * cfg["sample_rate"] / sr_native))
+    return raw, valid, max(expected, n_res)
+
+
+def process_files_basic(file_infos, cfg=BASIC_CONFIG, chroma="device", device=0):
+    """The basic script's per-file loop ([R] 1_preprocessing.py:223-258: load_audio_file + extract_all_features)
+    as batched device calls.  -> (features (N, 370) float64, ok (N,) bool, error text per file)."""
+    n = len(file_infos)
+    feats = np.full((n, 2 * cfg["n_mels"] + 2 * cfg.get("n_mfcc", 40) + 34), np.nan)
+    ok = np.zeros((n,), bool)
+    errors = [""] * n
+    groups, failed = _decode_groups(file_infos, cfg)
+    for i in failed:
+        errors[i] = "Failed to load"
+    for (sr_native, _ch), items in groups.items():
+        raw, valid, pad_to = _stack_group(items, sr_native, cfg)
+        try:
+            f, status = extract_all_features_batch(raw, cfg["sample_rate"], cfg, chroma, device, return_status=True,
+                                                   sr_in=sr_native, valid_frames=valid, pad_to=pad_to)
+        except Exception as e:
+            for i, _f in items:
+                errors[i] = str(e)
+            continue
+        for k, (i, _f) in enumerate(items):
+            if status[k]:
+                errors[i] = "Audio buffer is not finite everywhere"
+            else:
+                feats[i], ok[i] = f[k], True
+    return feats, ok, errors
+
+
+def process_files_advanced(file_infos, cfg=ADV_CONFIG, chroma="device", device=0):
+    """The advanced script's ``Parallel(...)(delayed(process_single_file)(f) ...)`` map ([R] _advanced.py:286-288)
+    as batched device calls: files are decoded on the host, grouped by (rate, channels) and run through the
+    host pipeline with per-clip lengths.  Returns the list of per-file dicts ``process_single_file`` returns."""
+    results = [None] * len(file_infos)
+    groups, failed = _decode_groups(file_infos, cfg)
+    for i in failed:
+        results[i] = {"status": "failed", "path": file_infos[i]["path"], "error": "Load failed"}
+    for (sr_native, _ch), items in groups.items():
+        raw, valid, pad_to = _stack_group(items, sr_native, cfg)
         try:
             mel, flat, status = process_batch_advanced(raw, cfg["sample_rate"], cfg, chroma, device, sr_in=sr_native,
-                                                       valid_frames=valid, pad_to=max(expected, n_res))
+                                                       valid_frames=valid, pad_to=pad_to)
         except Exception as e:
             for i, _f in items:
                 results[i] = {"status": "failed", "path": file_infos[i]["path"], "error": str(e)}
