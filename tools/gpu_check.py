@@ -43,6 +43,32 @@ run(40, 66150)                      # the mixture DESIGN.md quotes
 run(8, 66150, window="hamming")     # window table path (no synthesised Hann, no early copy)
 run(8, 66150, n_mels=40)
 run(8, 66150, power=1.0)
+# round 2: librosa.load's arithmetic on the device against the oracle (scipy.signal.resample_poly) ...
+from oracle import librosa_oracle as orc
+ex = hl.FeatureExtractor(n_mfcc=40, ref=np.max)
+rng = np.random.default_rng(5)
+for sr_in, ch in ((44100, 2), (48000, 1), (16000, 1), (22050, 2), (8000, 3)):
+    n = int(1.5 * sr_in) + 7
+    t = np.arange(n) / sr_in
+    x = np.stack([0.3 * np.sin(2 * np.pi * 330.0 * (c + 1) * t) + 0.05 * rng.standard_normal(n) for c in range(ch)], axis=1)
+    pcm = np.clip(np.rint(x * 32768.0), -32768, 32767).astype(np.int16)[None]
+    got = ex.load_frontend_device(torch.from_numpy(pcm).cuda(), sr_in=sr_in).cpu().numpy()[0]
+    want = orc.load_pcm16(pcm[0], sr_in, sr=22050)[0]
+    print(f"front end {sr_in} Hz x{ch} int16 -> 22050 Hz mono: {len(got)} samples, max abs diff vs scipy resample_poly {np.abs(got - want).max():.3g}", flush=True)
+# ... and the tabular normalisation against sklearn
+from sklearn.impute import SimpleImputer
+from sklearn.preprocessing import StandardScaler
+from hybrid_language_music_clustering_vae_b200.scaler import fit_transform_tabular_device, fit_transform_device
+X = rng.standard_normal((1336, 370)) * rng.uniform(0.1, 40.0, 370) + rng.uniform(-100, 100, 370)
+X[rng.integers(0, 1336, 40), rng.integers(0, 370, 40)] = np.nan
+X[rng.integers(0, 1336, 10), rng.integers(0, 370, 10)] = np.inf
+imp, scaled, _im, _sc = fit_transform_tabular_device(torch.from_numpy(X).cuda())
+wi = SimpleImputer(strategy="mean").fit_transform(np.where(np.isinf(X), np.nan, X))
+ws = StandardScaler().fit_transform(wi)
+print(f"tabular (1336, 370) f64: imputed max abs diff {np.abs(imp.cpu().numpy() - wi).max():.3g}, scaled max abs diff {np.abs(scaled.cpu().numpy() - ws).max():.3g}")
+M = (rng.standard_normal((200, 131072)) * 12 - 40).astype(np.float32)
+ym, _ = fit_transform_device(torch.from_numpy(M).cuda())
+print(f"mel scaler (200, 131072) f32: max abs diff vs sklearn {np.abs(ym.cpu().numpy() - StandardScaler().fit_transform(M)).max():.3g}", flush=True)
 # throughput quick look
 ex = hl.FeatureExtractor(n_mfcc=40, ref=np.max)
 y = torch.randn(2000, 66152, device="cuda")[:, :66150] * 0.1
