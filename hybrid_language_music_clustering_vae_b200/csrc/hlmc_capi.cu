@@ -59,6 +59,7 @@ struct hlmc_plan {
     int ncp = 0;
     // device tables
     float* d_fast = nullptr; FastTables ft{};
+    float* d_tmem_tab = nullptr;                                          // per-lane tables for Tensor Memory
     float* d_fast4 = nullptr; Fast4Tables ft4{}; bool fast4_ok = false;   // n_fft = 4096 register-FFT kernel
     float* d_win = nullptr; float2* d_twm = nullptr; float2* d_tws = nullptr;
     int* d_mel_lo = nullptr; int* d_mel_len = nullptr; int* d_mel_off = nullptr; float* d_mel_w = nullptr;
@@ -366,7 +367,7 @@ void hlmc_plan_destroy(hlmc_plan* plan) {
     free_slots(plan);
     for (auto e : plan->ev) cudaEventDestroy(e);
     for (auto& r : plan->resamplers) cudaFree(r.d_hpoly);
-    cudaFree(plan->d_fast); cudaFree(plan->d_fast4); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
+    cudaFree(plan->d_fast); cudaFree(plan->d_tmem_tab); cudaFree(plan->d_fast4); cudaFree(plan->d_win); cudaFree(plan->d_twm); cudaFree(plan->d_tws);
     cudaFree(plan->d_mel_lo); cudaFree(plan->d_mel_len); cudaFree(plan->d_mel_off); cudaFree(plan->d_mel_w);
     cudaFree(plan->d_dct_t); cudaFree(plan->d_chroma_fb); cudaFree(plan->d_edges);
     delete plan;
@@ -469,6 +470,10 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         const int kReadEnd = 1105;           // the kernel keeps scratch [0, 1105) finite
         build_banded_groups(pl->mel_dense, nm, F, kReadEnd, meta, melw);
         auto r4 = [](int x) { return (x + 3) & ~3; };
+        if (ng == 4 && meta[0] < 256 && meta[1] < 256 && meta[2] < 256 && meta[3] < 256 &&
+            meta[kMaxMelGroups + 1] == 128 * meta[0] && meta[kMaxMelGroups + 2] == 128 * (meta[0] + meta[1]) &&
+            meta[kMaxMelGroups + 3] == 128 * (meta[0] + meta[1] + meta[2]))
+            ft.mel_unr = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
         ft.tw1 = 0;
         ft.tw2 = ft.tw1 + 31 * 32 * 2;
         ft.hann_cs = ft.tw2 + 32 * 2;
@@ -505,6 +510,40 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         pl->ft = ft;
         UP(d_fast, blob)
         pl->fast_ok = fast_smem_bytes(ft, 8, N, p.hop_length, nm) <= 227 * 1024;
+        if (ft.mel_unr != 0) {
+            // the same tables per lane for Tensor Memory (frames_fast_2048<..., TM>): [32][cols]
+            int steps[4], pre[4], padded = 0;
+            for (int g = 0; g < 4; ++g) { steps[g] = meta[g]; pre[g] = padded; padded += (steps[g] + 3) & ~3; }
+            const int cols = kTmMel + 4 * padded;
+            if (cols <= kTmAlloc) {
+                std::vector<float> tm((size_t)32 * cols, 0.0f);
+                for (int l = 0; l < 32; ++l) {
+                    float* row = &tm[(size_t)l * cols];
+                    for (int j = 0; j < 32; ++j) {
+                        row[kTmWin + 2 * j] = win[2 * (l + 32 * j)];
+                        row[kTmWin + 2 * j + 1] = win[2 * (l + 32 * j) + 1];
+                    }
+                    for (int k1 = 1; k1 < 32; ++k1) {
+                        row[kTmTw1 + 2 * (k1 - 1)] = blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2];
+                        row[kTmTw1 + 2 * (k1 - 1) + 1] = blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 1];
+                    }
+                    for (int i = 0; i < 16; ++i) {
+                        const double th = 2.0 * M_PI * double(16 * l + i) / 2048.0;      // -i * W_2048^(16 l + i)
+                        row[kTmTw2 + 2 * i] = float(-sin(th));
+                        row[kTmTw2 + 2 * i + 1] = float(-cos(th));
+                    }
+                    for (int g = 0; g < 4; ++g) {
+                        memcpy(&row[kTmMeta + g], &meta[2 * kMaxMelGroups + 32 * g + l], 4);
+                        for (int st = 0; st < steps[g]; ++st)
+                            for (int c = 0; c < 4; ++c)
+                                row[kTmMel + 4 * (pre[g] + st) + c] = melw[(size_t)meta[kMaxMelGroups + g] + ((size_t)st * 32 + l) * 4 + c];
+                    }
+                }
+                UP(d_tmem_tab, tm)
+                pl->ft.tmem_tab = pl->d_tmem_tab;
+                pl->ft.tmem_cols = cols;
+            }
+        }
     }
     // register-FFT tables for n_fft = 4096 (frames_fast_4096): full-length periodic Hann, n_mels <= 128
     if (N == 4096) {

@@ -149,11 +149,11 @@ constexpr int kPrefBufFloats = kLandOff + kFastNfft + 4;
 struct FastSmemLayout {
     int bars, tables, ntab, wbuf, wb, total;   // float offsets; ntab = table floats staged; wb = floats per warp buffer
 };
-__host__ __device__ inline FastSmemLayout fast_layout(const FastTables& ft, int nw, bool pref) {
+__host__ __device__ inline FastSmemLayout fast_layout(const FastTables& ft, int nw, bool pref, bool tm = false) {
     FastSmemLayout L;
-    L.bars = 0;                                   // nw mbarriers, 8 B each
-    L.tables = (2 * nw + 3) & ~3;
-    L.ntab = pref ? ft.nowin : ft.total;          // PREF kernels synthesise the Hann window: no table
+    L.bars = 0;                                   // nw mbarriers, 8 B each (TM kernels: + the TMEM base address)
+    L.tables = (2 * nw + 3 + (tm ? 4 : 0)) & ~3;
+    L.ntab = tm ? 0 : pref ? ft.nowin : ft.total; // PREF kernels synthesise the Hann window: no table; TM kernels: all tables in TMEM
     L.wbuf = L.tables + L.ntab;
     const int scr = (ft.scr > kWarpBufFloats) ? ft.scr : kWarpBufFloats;
     L.wb = pref ? kPrefBufFloats : ((scr + 3) & ~3);
@@ -174,6 +174,38 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+// ---------------------------------------------------------------------------
+// Tensor Memory as a per-lane table store (TM kernels).  The per-lane read-only tables of the frame pipeline -
+// window, inter-pass twiddles, split twiddles, banded mel weights, gather start offsets - cost 166 of the 655
+// shared-memory wavefronts per frame when they are read with LDS, on the pipe that bounds the kernel.  TMEM is
+// a second on-chip memory with its own read path (measured: 256 B/clk/SM, and concurrent with LDS traffic at
+// full rate - tools/tmem_lut_bench.cu): thread i of a warp reads N consecutive 32-bit columns of TMEM lane
+// 32*(warp%4) + i with ONE tcgen05.ld.32x32b.xN.  Every 32-lane quarter holds the same 32 x kTmCols table.
+// Column map (floats, per lane):
+// (kTmWin ... kTmAlloc: hlmc_internal.h)
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// The loaded registers are valid only after tcgen05.wait::ld; naming them as in/out operands keeps every use behind it.
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+        : "r"(taddr));
+}
+__device__ __forceinline__ float2 f2_of(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 // Banded mel gather of one (group, lane): n4 float4 steps of 4 taps each.  The step count is
 // warp-uniform but only known at run time.  Steps are taken in straight-line chunks of 4, 2 and 1 so
@@ -205,6 +237,66 @@ __device__ __forceinline__ void mel_steps(int n4, const float4* __restrict__ wp,
     if (n4 & 1) mel_chunk<1, WS>(wp, pp, a01, a23);
 }
 
+// Compile-time step counts (the default plan: 128 Slaney mels at 22.05 kHz -> 3, 3, 7, 14 float4 steps for the
+// four filter groups): the same chunks as mel_steps, but every trip count, weight offset and shared-memory
+// offset is an immediate - no loop control, no tail tests, no per-group table look-ups.
+constexpr int kMelUnrDefault = 3 | (3 << 8) | (7 << 16) | (14 << 24);
+template <int STEPS, int WS = 32>
+__device__ __forceinline__ void mel_steps_unrolled(const float4* __restrict__ wp, const float* __restrict__ pp,
+                                                   float2& a01, float2& a23) {
+    constexpr int C4 = STEPS / 4;
+#pragma unroll
+    for (int c = 0; c < C4; ++c) mel_chunk<4, WS>(wp + 4 * WS * c, pp + 16 * c, a01, a23);
+    if constexpr ((STEPS & 3) == 3) mel_chunk<3, WS>(wp + 4 * WS * C4, pp + 16 * C4, a01, a23);
+    if constexpr ((STEPS & 3) == 2) mel_chunk<2, WS>(wp + 4 * WS * C4, pp + 16 * C4, a01, a23);
+    if constexpr ((STEPS & 3) == 1) mel_chunk<1, WS>(wp + 4 * WS * C4, pp + 16 * C4, a01, a23);
+}
+template <int UNR, int G>
+__device__ __forceinline__ float mel_group_unrolled(const float* __restrict__ s_melw, const int* __restrict__ s_meta,
+                                                    const float* __restrict__ sc, int lane) {
+    constexpr int STEPS = (UNR >> (8 * G)) & 255;
+    constexpr int GOFF = 128 * ((G > 0 ? (UNR & 255) : 0) + (G > 1 ? ((UNR >> 8) & 255) : 0) + (G > 2 ? ((UNR >> 16) & 255) : 0));
+    const float4* wp = reinterpret_cast<const float4*>(s_melw + GOFF) + lane;
+    const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * G + lane];
+    float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
+    mel_steps_unrolled<STEPS>(wp, pp, a01, a23);
+    a01 = __fadd2_rn(a01, a23);
+    return a01.x + a01.y;
+}
+
+// One filter group with its weights in TMEM: chunks of 4 steps = one tcgen05.ld.x16; the 16 power-spectrum loads
+// of the chunk are in flight while it lands.  PS = the group's steps rounded up to whole chunks (table padding).
+template <int UNR, int G>
+__device__ __forceinline__ float mel_group_tm(uint32_t tq, const float* __restrict__ pp) {
+    constexpr int STEPS = (UNR >> (8 * G)) & 255;
+    constexpr int pad4 = 3;
+    constexpr int COL = kTmMel + 4 * ((G > 0 ? (((UNR & 255) + pad4) & ~3) : 0) + (G > 1 ? ((((UNR >> 8) & 255) + pad4) & ~3) : 0) +
+                                      (G > 2 ? ((((UNR >> 16) & 255) + pad4) & ~3) : 0));
+    float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
+#pragma unroll
+    for (int c = 0; c < (STEPS + 3) / 4; ++c) {
+        constexpr int dummy = 0; (void)dummy;
+        uint32_t wr[16];
+        tmem_ld16_issue(tq + COL + 16 * c, wr);
+        float2 p01[4], p23[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (4 * c + u < STEPS) {
+                p01[u] = make_float2(pp[16 * c + 4 * u + 0], pp[16 * c + 4 * u + 1]);
+                p23[u] = make_float2(pp[16 * c + 4 * u + 2], pp[16 * c + 4 * u + 3]);
+            }
+        tmem_wait16(wr);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (4 * c + u < STEPS) {
+                a01 = __ffma2_rn(f2_of(wr[4 * u], wr[4 * u + 1]), p01[u], a01);
+                a23 = __ffma2_rn(f2_of(wr[4 * u + 2], wr[4 * u + 3]), p23[u], a23);
+            }
+    }
+    a01 = __fadd2_rn(a01, a23);
+    return a01.x + a01.y;
+}
+
 struct WarpState {
     float* sc;                 // this warp's shared buffer (TMA landing zone, then scratch)
     float2* sc2;
@@ -213,6 +305,7 @@ struct WarpState {
     const float2 *s_win, *s_tw1, *s_tw2;
     const float4* s_hcs;       // per-lane (cos, cos', sin, sin') of the Hann phase (PREF kernels)
     int lane, zw_base, zlo_base, zhi_base, zhi0;
+    uint32_t tq;               // TMEM address of this warp's 32-lane quarter (TM kernels)
     bool pending;              // a TMA copy of the next frame to process is in flight (PREF kernels)
     int pend_off;              // its alignment shift
 };
@@ -252,7 +345,7 @@ __device__ __forceinline__ int issue_frame_tma(const FrameArgs& a, const WarpSta
 // frees pay for (2) a landing zone of its own, so the TMA copy of the warp's NEXT frame (nclip, nt) is
 // started as soon as the transposes are done and flies while the statistics and the mel projection of
 // this frame run - the wait at the top of the next frame is then (nearly) free.
-template <bool PREF>
+template <bool PREF, bool TM = false>
 __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
                                                const float* nclip, int nt,
                                                float2 (&P)[16], float2 (&S)[16], float& p512, float& s512,
@@ -311,6 +404,30 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     float2 v[32];
 
     // ---- phase 0: frame -> registers; window; RMS and ZCR partials
+    if constexpr (TM) {
+        // the window comes from TMEM, 8 sample pairs at a time (their LDS are in flight while the tcgen05.ld lands)
+        const float2* xp = reinterpret_cast<const float2*>(land + off);
+        const float2 zt = make_float2(zthr, zthr);
+        float2 ss2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int jc = 0; jc < 4; ++jc) {
+            uint32_t wr[16];
+            tmem_ld16_issue(w.tq + kTmWin + 16 * jc, wr);
+            float2 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = xp[lane + 32 * (8 * jc + u)];
+            tmem_wait16(wr);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                ss2 = __ffma2_rn(x[u], x[u], ss2);
+                const float2 xt = __fadd2_rn(x[u], zt);
+                za = __funnelshift_l(__float_as_uint(xt.x), za, 1);
+                zb = __funnelshift_l(__float_as_uint(xt.y), zb, 1);
+                v[8 * jc + u] = __fmul2_rn(x[u], f2_of(wr[2 * u], wr[2 * u + 1]));
+            }
+        }
+        ss = ss2.x + ss2.y;
+    } else
     {
         const float2* xp = reinterpret_cast<const float2*>(land + off);
         const float2 zt = make_float2(zthr, zthr);
@@ -356,11 +473,28 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     fftreg2::fft_dif<32>(v);
 
     // ---- phase 2: inter-pass twiddle W_1024^(lane*k1); the table holds (cos, -sin)
+    if constexpr (TM) {
 #pragma unroll
-    for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 tw = s_tw1[(k1 - 1) * 32 + lane];
-        const int p = pos32(k1);
-        v[p] = fftreg2::cmul(v[p], tw.x, tw.y);
+        for (int kc = 0; kc < 4; ++kc) {
+            uint32_t tr[16];
+            tmem_ld16_issue(w.tq + kTmTw1 + 16 * kc, tr);
+            tmem_wait16(tr);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k1 = 8 * kc + u + 1;
+                if (k1 < 32) {
+                    const int p = pos32(k1);
+                    v[p] = fftreg2::cmul(v[p], __uint_as_float(tr[2 * u]), __uint_as_float(tr[2 * u + 1]));
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+            const float2 tw = s_tw1[(k1 - 1) * 32 + lane];
+            const int p = pos32(k1);
+            v[p] = fftreg2::cmul(v[p], tw.x, tw.y);
+        }
     }
 
     // ---- phase 3: 32x32 complex transpose through shared memory
@@ -396,10 +530,20 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
 
     // ---- phase 6: real-FFT split, |X|^2 and |X|, local moments of |X|
     float2 M0 = make_float2(0.f, 0.f), M1 = M0, M2 = M0;
-    const float2 tw_base = s_tw2[lane];            // -i * W_2048^(16*lane); bin 16*lane + i needs it times W_2048^i
+    float2 tw_base = make_float2(0.f, 0.f);        // -i * W_2048^(16*lane); bin 16*lane + i needs it times W_2048^i
+    uint32_t t2a[16], t2b[16];
+    if constexpr (TM) {
+        tmem_ld16_issue(w.tq + kTmTw2, t2a);
+        tmem_ld16_issue(w.tq + kTmTw2 + 16, t2b);
+        tmem_wait16(t2a);
+        tmem_wait16(t2b);
+    } else {
+        tw_base = s_tw2[lane];
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const float2 tw = (i == 0) ? tw_base
+        const float2 tw = TM ? (i < 8 ? f2_of(t2a[2 * i], t2a[2 * i + 1]) : f2_of(t2b[2 * (i - 8)], t2b[2 * (i - 8) + 1]))
+                        : (i == 0) ? tw_base
                                    : fftreg2::cmul_conj(tw_base, float(fftreg::cos2pi(i, 2048)), float(fftreg::sin2pi(i, 2048)));
         const float2 za_ = v[i], zb_ = v[16 + i];
         const float2 e = __fadd2_rn(za_, make_float2(zb_.x, -zb_.y));      // Z[k] + conj Z[1024-k]
@@ -422,13 +566,14 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     s512 = fast_sqrt(p512);
 }
 
-template <int NW, bool PIP, bool PREF>
+template <int NW, bool PIP, bool PREF, int UNR = 0, bool TM = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
+    static_assert(!TM || (PREF && UNR != 0 && !PIP), "TM kernels: default window path, compile-time mel steps");
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const FastSmemLayout L = fast_layout(ft, NW, PREF);
+    const FastSmemLayout L = fast_layout(ft, NW, PREF, TM);
 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
     float* tab = smem + L.tables;
@@ -448,7 +593,31 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         mbar_init(mbar, 1);
         fence_mbar_init();
     }
+    uint32_t tbase = 0;
+    if constexpr (TM) {
+        // all of this SM's Tensor Memory; warp q fills lanes 32q..32q+31 with the per-lane tables
+        uint32_t* s_taddr = reinterpret_cast<uint32_t*>(smem + 2 * NW);
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_taddr)), "r"(kTmAlloc));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        tbase = *s_taddr;
+        if (warp < 4) {
+            const float4* src = reinterpret_cast<const float4*>(ft.tmem_tab + (size_t)lane * ft.tmem_cols);
+            for (int c = 0; c < ft.tmem_cols; c += 4) {
+                const float4 q = __ldg(src + c / 4);
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tbase + ((uint32_t)(32 * warp) << 16) + c),
+                             "r"(__float_as_uint(q.x)), "r"(__float_as_uint(q.y)), "r"(__float_as_uint(q.z)), "r"(__float_as_uint(q.w)));
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+    }
     __syncthreads();
+    if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- frame assignment: the CTA owns a contiguous run of (clip, frame) pairs and its NW warps
     //      take them round-robin, so at any moment one SM works on NW neighbouring frames of one
@@ -458,7 +627,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     const long long c0 = (long long)blockIdx.x * per_cta;
     const long long g1 = (c0 + per_cta < total) ? c0 + per_cta : total;
     const long long g0 = c0 + warp;
-    if (g0 >= g1) return;
+    if (!TM && g0 >= g1) return;                 // (TM kernels: every warp stays for the TMEM deallocation)
     int b = (int)(g0 / a.T);
     int t = (int)(g0 - (long long)b * a.T);
     float clip_max = 0.0f;
@@ -466,6 +635,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     w.sc = sc; w.sc2 = sc2; w.mbar = mbar; w.parity = 0;
     w.s_win = s_win; w.s_tw1 = s_tw1; w.s_tw2 = s_tw2; w.lane = lane;
     w.s_hcs = reinterpret_cast<const float4*>(tab + ft.hann_cs);
+    w.tq = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
     w.pending = false; w.pend_off = 0;
     // per-lane bases of the regroup buffer, layout p(k) = k + k/16 in float2 units: every
     // access is base + immediate and conflict-free (17 is odd)
@@ -483,7 +653,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         float2 P[16], S[16];
         float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
         int zc;
-        frame_spectrum<PREF>(a, w, clip, t, nclip, nt, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
+        frame_spectrum<PREF, TM>(a, w, clip, t, nclip, nt, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
 
         // ---- chroma_stft: keep the power spectrum for the projection that follows the tuning estimate
         //      (8 coalesced 16-byte stores per lane, in the lane's register order: no second STFT pass)
@@ -631,6 +801,30 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
             float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
                                             : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+            if constexpr (TM) {
+                uint32_t st4[4];
+                tmem_ld4(w.tq + kTmMeta, st4);       // the lane's first tap in each group
+                const float acc0 = mel_group_tm<UNR, 0>(w.tq, sc + st4[0]);
+                const float acc1 = mel_group_tm<UNR, 1>(w.tq, sc + st4[1]);
+                const float acc2 = mel_group_tm<UNR, 2>(w.tq, sc + st4[2]);
+                const float acc3 = mel_group_tm<UNR, 3>(w.tq, sc + st4[3]);
+                outb[(size_t)lane * mstride] = acc0;
+                outb[(size_t)(32 + lane) * mstride] = acc1;
+                outb[(size_t)(64 + lane) * mstride] = acc2;
+                outb[(size_t)(96 + lane) * mstride] = acc3;
+                wmax = fmaxf(fmaxf(acc0, acc1), fmaxf(acc2, acc3));
+            } else if constexpr (UNR != 0) {
+                // four groups of 32 filters (n_mels = 128), step counts known at compile time
+                const float acc0 = mel_group_unrolled<UNR, 0>(s_melw, s_meta, sc, lane);
+                const float acc1 = mel_group_unrolled<UNR, 1>(s_melw, s_meta, sc, lane);
+                const float acc2 = mel_group_unrolled<UNR, 2>(s_melw, s_meta, sc, lane);
+                const float acc3 = mel_group_unrolled<UNR, 3>(s_melw, s_meta, sc, lane);
+                outb[(size_t)lane * mstride] = acc0;
+                outb[(size_t)(32 + lane) * mstride] = acc1;
+                outb[(size_t)(64 + lane) * mstride] = acc2;
+                outb[(size_t)(96 + lane) * mstride] = acc3;
+                wmax = fmaxf(fmaxf(acc0, acc1), fmaxf(acc2, acc3));
+            } else
             for (int g = 0; g < ft.n_groups; ++g) {
                 const int n4 = s_meta[g];
                 const float4* wp = reinterpret_cast<const float4*>(s_melw + s_meta[kMaxMelGroups + g]) + lane;
@@ -667,20 +861,25 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         t = nt; b = nb;
         __syncwarp();                       // scratch reads are done before the next frame lands
     }
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kTmAlloc));
+    }
 }
 
-template <int NW, bool PIP, bool PREF>
+template <int NW, bool PIP, bool PREF, int UNR = 0, bool TM = false>
 static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                   int num_sms, cudaStream_t stream) {
-    const int smem = fast_layout(ft, NW, PREF).total * 4;
-    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP, PREF>,
+    const int smem = fast_layout(ft, NW, PREF, TM).total * 4;
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP, PREF, UNR, TM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long frames = (long long)a.B * a.T;
     if (frames <= 0) return cudaSuccess;
     long long grid = (frames + NW - 1) / NW;
     if (grid > num_sms) grid = num_sms;
-    frames_fast_2048<NW, PIP, PREF><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    frames_fast_2048<NW, PIP, PREF, UNR, TM><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
@@ -691,6 +890,15 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
     constexpr int kMaxSmem = 227 * 1024;
     // default window: 16 warps with the next frame's copy in flight (Hann synthesised in registers)
     static const bool no_pref = [] { const char* e = getenv("HLMC_NO_PREF"); return e && e[0] == '1'; }();
+    // the default plan (128 mels, step counts 3 / 3 / 7 / 14): mel gather with compile-time trip counts
+    static const bool no_unr = [] { const char* e = getenv("HLMC_NO_UNROLL"); return e && e[0] == '1'; }();
+    static const bool no_tm = [] { const char* e = getenv("HLMC_NO_TMEM"); return e && e[0] == '1'; }();
+    if (!no_pref && !no_tm && !pip && ft.tmem_tab != nullptr && ft.mel_unr == kMelUnrDefault && a.n_mels == 128 &&
+        a.mel_out != nullptr)
+        return launch_fast_nw<16, false, true, kMelUnrDefault, true>(a, d_tables, ft, num_sms, stream);
+    if (!no_pref && !no_unr && !pip && ft.hann && ft.mel_unr == kMelUnrDefault && a.n_mels == 128 &&
+        fast_layout(ft, 16, true).total * 4 <= kMaxSmem)
+        return launch_fast_nw<16, false, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream);
     if (!no_pref && ft.hann && fast_layout(ft, 16, true).total * 4 <= kMaxSmem)
         return pip ? launch_fast_nw<16, true, true>(a, d_tables, ft, num_sms, stream)
                    : launch_fast_nw<16, false, true>(a, d_tables, ft, num_sms, stream);

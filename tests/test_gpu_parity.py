@@ -264,7 +264,10 @@ def test_script_level_functions_and_layout(built, tmp_path):
     assert np.all(d <= tol), np.nonzero(d > tol)
     assert np.all(pp.extract_all_features(y[0], SR, chroma="zeros")[346:] == 0.0)   # explicit policy, logged
     fb = pp.extract_all_features_batch(y, SR, chroma="nan")
-    assert fb.shape == (5, 370) and np.isnan(fb[:, 346:]).all() and np.array_equal(fb[0, :346], f[:346])
+    # (f came through the kernel variant with the piptrack epilogue, which synthesises the Hann window in registers;
+    #  fb through the default variant, which reads the window from its table: equal to rounding, not bitwise)
+    assert fb.shape == (5, 370) and np.isnan(fb[:, 346:]).all()
+    assert np.allclose(fb[0, :346], f[:346], rtol=1e-5, atol=1e-5)
     fb = pp.extract_all_features_batch(y, SR)
     # 1_preprocessing_advanced.py
     mel, flat, status = pp.process_batch_advanced(y, SR)
