@@ -470,10 +470,7 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         const int kReadEnd = 1105;           // the kernel keeps scratch [0, 1105) finite
         build_banded_groups(pl->mel_dense, nm, F, kReadEnd, meta, melw);
         auto r4 = [](int x) { return (x + 3) & ~3; };
-        if (ng == 4 && meta[0] < 256 && meta[1] < 256 && meta[2] < 256 && meta[3] < 256 &&
-            meta[kMaxMelGroups + 1] == 128 * meta[0] && meta[kMaxMelGroups + 2] == 128 * (meta[0] + meta[1]) &&
-            meta[kMaxMelGroups + 3] == 128 * (meta[0] + meta[1] + meta[2]))
-            ft.mel_unr = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
+        for (int g = 0; g < ng; ++g) ft.mel_steps[g] = meta[g];
         ft.tw1 = 0;
         ft.tw2 = ft.tw1 + 31 * 32 * 2;
         ft.hann_cs = ft.tw2 + 32 * 2;
@@ -510,11 +507,12 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
         pl->ft = ft;
         UP(d_fast, blob)
         pl->fast_ok = fast_smem_bytes(ft, 8, N, p.hop_length, nm) <= 227 * 1024;
-        if (ft.mel_unr != 0) {
-            // the same tables per lane for Tensor Memory (frames_fast_2048<..., TM>): [32][cols]
-            int steps[4], pre[4], padded = 0;
-            for (int g = 0; g < 4; ++g) { steps[g] = meta[g]; pre[g] = padded; padded += (steps[g] + 3) & ~3; }
-            const int cols = kTmMel + 4 * padded;
+        {
+            // the same tables per lane for Tensor Memory (frames_fast_2048<..., TM>): [32][cols], see kTm* in
+            // hlmc_internal.h; built whenever the banded weights fit the 512 columns
+            int total_steps = 0;
+            for (int g = 0; g < ng; ++g) total_steps += meta[g];
+            const int cols = kTmMel + 4 * total_steps;
             if (cols <= kTmAlloc) {
                 std::vector<float> tm((size_t)32 * cols, 0.0f);
                 for (int l = 0; l < 32; ++l) {
@@ -532,11 +530,13 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
                         row[kTmTw2 + 2 * i] = float(-sin(th));
                         row[kTmTw2 + 2 * i + 1] = float(-cos(th));
                     }
-                    for (int g = 0; g < 4; ++g) {
+                    int pre = 0;
+                    for (int g = 0; g < ng; ++g) {
                         memcpy(&row[kTmMeta + g], &meta[2 * kMaxMelGroups + 32 * g + l], 4);
-                        for (int st = 0; st < steps[g]; ++st)
+                        for (int st = 0; st < meta[g]; ++st)
                             for (int c = 0; c < 4; ++c)
-                                row[kTmMel + 4 * (pre[g] + st) + c] = melw[(size_t)meta[kMaxMelGroups + g] + ((size_t)st * 32 + l) * 4 + c];
+                                row[kTmMel + 4 * (pre + st) + c] = melw[(size_t)meta[kMaxMelGroups + g] + ((size_t)st * 32 + l) * 4 + c];
+                        pre += meta[g];
                     }
                 }
                 UP(d_tmem_tab, tm)

@@ -24,7 +24,7 @@ struct FastTables {
     int hann;       // 1: the window is the full-length periodic Hann (n_fft 2048: synthesised in registers)
     int hann_cs;    // 32 float4: (cos, cos', sin, sin') of 2*pi*(2*lane + {0,1}) / n_fft
     int nowin;      // floats before the window (multiple of 4)
-    int mel_unr;    // n_fft 2048, n_groups == 4: the four groups' float4 step counts packed one per byte, else 0
+    int mel_steps[kMaxMelGroups];   // float4 steps per filter group (TM kernels read them from the kernel parameters)
     // per-lane tables for Tensor Memory (TM kernels; global memory, [32 lanes][tmem_cols] floats) or NULL
     const float* tmem_tab;
     int tmem_cols;  // multiple of 4, <= 512
@@ -46,8 +46,8 @@ struct Fast4Tables {
 constexpr int kTmWin = 0;       // 64: 0.5*window[2(lane+32j)], 0.5*window[2(lane+32j)+1], j = 0..31
 constexpr int kTmTw1 = 64;      // 64: W_1024^(lane*k1) as (cos, -sin), k1 = 1..31 (last pair unused)
 constexpr int kTmTw2 = 128;     // 32: -i*W_2048^(16*lane + i), i = 0..15
-constexpr int kTmMeta = 160;    // 4 (+4 pad): first tap of the lane's filter in each of the four groups (int32 bits)
-constexpr int kTmMel = 168;     // banded mel weights, float4 per step, every group padded to whole chunks of 4 steps
+constexpr int kTmMeta = 160;    // 8: first tap of the lane's filter in each of the (up to 8) groups (int32 bits)
+constexpr int kTmMel = 168;     // banded mel weights, float4 per step, group after group
 constexpr int kTmAlloc = 512;   // columns allocated (all of TMEM: one CTA per SM)
 
 struct FrameArgs {

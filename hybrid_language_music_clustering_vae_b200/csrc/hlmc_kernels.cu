@@ -237,62 +237,68 @@ __device__ __forceinline__ void mel_steps(int n4, const float4* __restrict__ wp,
     if (n4 & 1) mel_chunk<1, WS>(wp, pp, a01, a23);
 }
 
-// Compile-time step counts (the default plan: 128 Slaney mels at 22.05 kHz -> 3, 3, 7, 14 float4 steps for the
-// four filter groups): the same chunks as mel_steps, but every trip count, weight offset and shared-memory
-// offset is an immediate - no loop control, no tail tests, no per-group table look-ups.
-constexpr int kMelUnrDefault = 3 | (3 << 8) | (7 << 16) | (14 << 24);
-template <int STEPS, int WS = 32>
-__device__ __forceinline__ void mel_steps_unrolled(const float4* __restrict__ wp, const float* __restrict__ pp,
-                                                   float2& a01, float2& a23) {
-    constexpr int C4 = STEPS / 4;
-#pragma unroll
-    for (int c = 0; c < C4; ++c) mel_chunk<4, WS>(wp + 4 * WS * c, pp + 16 * c, a01, a23);
-    if constexpr ((STEPS & 3) == 3) mel_chunk<3, WS>(wp + 4 * WS * C4, pp + 16 * C4, a01, a23);
-    if constexpr ((STEPS & 3) == 2) mel_chunk<2, WS>(wp + 4 * WS * C4, pp + 16 * C4, a01, a23);
-    if constexpr ((STEPS & 3) == 1) mel_chunk<1, WS>(wp + 4 * WS * C4, pp + 16 * C4, a01, a23);
+// Mel gather with the weights in Tensor Memory: CH steps = one tcgen05.ld of 4*CH columns; the power-spectrum
+// loads of the chunk are in flight while it lands.
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
 }
-template <int UNR, int G>
-__device__ __forceinline__ float mel_group_unrolled(const float* __restrict__ s_melw, const int* __restrict__ s_meta,
-                                                    const float* __restrict__ sc, int lane) {
-    constexpr int STEPS = (UNR >> (8 * G)) & 255;
-    constexpr int GOFF = 128 * ((G > 0 ? (UNR & 255) : 0) + (G > 1 ? ((UNR >> 8) & 255) : 0) + (G > 2 ? ((UNR >> 16) & 255) : 0));
-    const float4* wp = reinterpret_cast<const float4*>(s_melw + GOFF) + lane;
-    const float* pp = sc + s_meta[2 * kMaxMelGroups + 32 * G + lane];
-    float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
-    mel_steps_unrolled<STEPS>(wp, pp, a01, a23);
-    a01 = __fadd2_rn(a01, a23);
-    return a01.x + a01.y;
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
+template <int CH>
+__device__ __forceinline__ void mel_chunk_tm(uint32_t taddr, const float* __restrict__ pp, float2& a01, float2& a23) {
+    uint32_t wr[16];
+    if constexpr (CH == 4) tmem_ld16_issue(taddr, wr);
+    else if constexpr (CH == 2) tmem_ld8_issue(taddr, wr);
+    else tmem_ld4_issue(taddr, wr);
+    float2 p01[CH], p23[CH];
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+        p01[u] = make_float2(pp[4 * u + 0], pp[4 * u + 1]);
+        p23[u] = make_float2(pp[4 * u + 2], pp[4 * u + 3]);
+    }
+    if constexpr (CH == 4) tmem_wait16(wr);
+    else {
+        // (only the registers the load wrote are named: the others hold nothing)
+        if constexpr (CH == 2)
+            asm volatile("tcgen05.wait::ld.sync.aligned;"
+                         : "+r"(wr[0]), "+r"(wr[1]), "+r"(wr[2]), "+r"(wr[3]), "+r"(wr[4]), "+r"(wr[5]), "+r"(wr[6]), "+r"(wr[7]));
+        else
+            asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(wr[0]), "+r"(wr[1]), "+r"(wr[2]), "+r"(wr[3]));
+    }
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+        a01 = __ffma2_rn(f2_of(wr[4 * u], wr[4 * u + 1]), p01[u], a01);
+        a23 = __ffma2_rn(f2_of(wr[4 * u + 2], wr[4 * u + 3]), p23[u], a23);
+    }
+}
+// n4 steps of one group; `col` = the group's first TMEM column
+__device__ __forceinline__ void mel_steps_tm(int n4, uint32_t taddr, const float* __restrict__ pp, float2& a01, float2& a23) {
+    for (; n4 >= 4; n4 -= 4, taddr += 16, pp += 16) mel_chunk_tm<4>(taddr, pp, a01, a23);
+    if (n4 & 2) { mel_chunk_tm<2>(taddr, pp, a01, a23); taddr += 8; pp += 8; }
+    if (n4 & 1) mel_chunk_tm<1>(taddr, pp, a01, a23);
 }
 
-// One filter group with its weights in TMEM: chunks of 4 steps = one tcgen05.ld.x16; the 16 power-spectrum loads
-// of the chunk are in flight while it lands.  PS = the group's steps rounded up to whole chunks (table padding).
+// The default plan (128 Slaney mels at 22.05 kHz: 3, 3, 7, 14 float4 steps for the four filter groups) gets its step
+// counts at compile time: every trip count and TMEM column is an immediate (measured: 3.80 against 4.03 ms).
+constexpr int kMelUnrDefault = 3 | (3 << 8) | (7 << 16) | (14 << 24);
 template <int UNR, int G>
 __device__ __forceinline__ float mel_group_tm(uint32_t tq, const float* __restrict__ pp) {
     constexpr int STEPS = (UNR >> (8 * G)) & 255;
-    constexpr int pad4 = 3;
-    constexpr int COL = kTmMel + 4 * ((G > 0 ? (((UNR & 255) + pad4) & ~3) : 0) + (G > 1 ? ((((UNR >> 8) & 255) + pad4) & ~3) : 0) +
-                                      (G > 2 ? ((((UNR >> 16) & 255) + pad4) & ~3) : 0));
+    constexpr int COL = kTmMel + 4 * ((G > 0 ? (UNR & 255) : 0) + (G > 1 ? ((UNR >> 8) & 255) : 0) + (G > 2 ? ((UNR >> 16) & 255) : 0));
     float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
 #pragma unroll
-    for (int c = 0; c < (STEPS + 3) / 4; ++c) {
-        constexpr int dummy = 0; (void)dummy;
-        uint32_t wr[16];
-        tmem_ld16_issue(tq + COL + 16 * c, wr);
-        float2 p01[4], p23[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (4 * c + u < STEPS) {
-                p01[u] = make_float2(pp[16 * c + 4 * u + 0], pp[16 * c + 4 * u + 1]);
-                p23[u] = make_float2(pp[16 * c + 4 * u + 2], pp[16 * c + 4 * u + 3]);
-            }
-        tmem_wait16(wr);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (4 * c + u < STEPS) {
-                a01 = __ffma2_rn(f2_of(wr[4 * u], wr[4 * u + 1]), p01[u], a01);
-                a23 = __ffma2_rn(f2_of(wr[4 * u + 2], wr[4 * u + 3]), p23[u], a23);
-            }
+    for (int c = 0; c < STEPS / 4; ++c) mel_chunk_tm<4>(tq + COL + 16 * c, pp + 16 * c, a01, a23);
+    if constexpr ((STEPS & 3) == 3) {
+        mel_chunk_tm<2>(tq + COL + 16 * (STEPS / 4), pp + 16 * (STEPS / 4), a01, a23);
+        mel_chunk_tm<1>(tq + COL + 16 * (STEPS / 4) + 8, pp + 16 * (STEPS / 4) + 8, a01, a23);
     }
+    if constexpr ((STEPS & 3) == 2) mel_chunk_tm<2>(tq + COL + 16 * (STEPS / 4), pp + 16 * (STEPS / 4), a01, a23);
+    if constexpr ((STEPS & 3) == 1) mel_chunk_tm<1>(tq + COL + 16 * (STEPS / 4), pp + 16 * (STEPS / 4), a01, a23);
     a01 = __fadd2_rn(a01, a23);
     return a01.x + a01.y;
 }
@@ -474,17 +480,22 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
 
     // ---- phase 2: inter-pass twiddle W_1024^(lane*k1); the table holds (cos, -sin)
     if constexpr (TM) {
+        // two tcgen05.ld in flight per wait (the wait drains every outstanding load)
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-            uint32_t tr[16];
+        for (int kc = 0; kc < 4; kc += 2) {
+            uint32_t tr[16], tr2[16];
             tmem_ld16_issue(w.tq + kTmTw1 + 16 * kc, tr);
+            tmem_ld16_issue(w.tq + kTmTw1 + 16 * kc + 16, tr2);
             tmem_wait16(tr);
+            tmem_wait16(tr2);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 const int k1 = 8 * kc + u + 1;
                 if (k1 < 32) {
                     const int p = pos32(k1);
-                    v[p] = fftreg2::cmul(v[p], __uint_as_float(tr[2 * u]), __uint_as_float(tr[2 * u + 1]));
+                    const uint32_t c = (u < 8) ? tr[2 * (u & 7)] : tr2[2 * (u & 7)];
+                    const uint32_t sn = (u < 8) ? tr[2 * (u & 7) + 1] : tr2[2 * (u & 7) + 1];
+                    v[p] = fftreg2::cmul(v[p], __uint_as_float(c), __uint_as_float(sn));
                 }
             }
         }
@@ -566,10 +577,11 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     s512 = fast_sqrt(p512);
 }
 
-template <int NW, bool PIP, bool PREF, int UNR = 0, bool TM = false>
+template <int NW, bool PIP, bool PREF, bool TM = false, int UNR = 0>
 __global__ void __launch_bounds__(NW * 32, 1)
 frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
-    static_assert(!TM || (PREF && UNR != 0 && !PIP), "TM kernels: default window path, compile-time mel steps");
+    static_assert(!TM || PREF, "TM kernels use the layout with a landing zone of its own");
+    static_assert(UNR == 0 || TM, "compile-time mel step counts: TM kernels only");
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -801,7 +813,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
             float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
                                             : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
-            if constexpr (TM) {
+            if constexpr (TM && UNR != 0) {
                 uint32_t st4[4];
                 tmem_ld4(w.tq + kTmMeta, st4);       // the lane's first tap in each group
                 const float acc0 = mel_group_tm<UNR, 0>(w.tq, sc + st4[0]);
@@ -813,17 +825,26 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 outb[(size_t)(64 + lane) * mstride] = acc2;
                 outb[(size_t)(96 + lane) * mstride] = acc3;
                 wmax = fmaxf(fmaxf(acc0, acc1), fmaxf(acc2, acc3));
-            } else if constexpr (UNR != 0) {
-                // four groups of 32 filters (n_mels = 128), step counts known at compile time
-                const float acc0 = mel_group_unrolled<UNR, 0>(s_melw, s_meta, sc, lane);
-                const float acc1 = mel_group_unrolled<UNR, 1>(s_melw, s_meta, sc, lane);
-                const float acc2 = mel_group_unrolled<UNR, 2>(s_melw, s_meta, sc, lane);
-                const float acc3 = mel_group_unrolled<UNR, 3>(s_melw, s_meta, sc, lane);
-                outb[(size_t)lane * mstride] = acc0;
-                outb[(size_t)(32 + lane) * mstride] = acc1;
-                outb[(size_t)(64 + lane) * mstride] = acc2;
-                outb[(size_t)(96 + lane) * mstride] = acc3;
-                wmax = fmaxf(fmaxf(acc0, acc1), fmaxf(acc2, acc3));
+            } else if constexpr (TM) {
+                uint32_t st4[4], st8[4];
+                tmem_ld4(w.tq + kTmMeta, st4);       // the lane's first tap in each group
+                if (ft.n_groups > 4) tmem_ld4(w.tq + kTmMeta + 4, st8);
+                uint32_t col = w.tq + kTmMel;
+#pragma unroll
+                for (int g = 0; g < kMaxMelGroups; ++g) {
+                    if (g < ft.n_groups) {
+                        const int n4 = ft.mel_steps[g];
+                        const float* pp = sc + (g < 4 ? st4[g & 3] : st8[g & 3]);
+                        float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
+                        mel_steps_tm(n4, col, pp, a01, a23);
+                        col += 4 * n4;
+                        a01 = __fadd2_rn(a01, a23);
+                        const float acc = a01.x + a01.y;
+                        const int m = 32 * g + lane;
+                        if (m < a.n_mels) outb[(size_t)m * mstride] = acc;
+                        wmax = fmaxf(wmax, acc);
+                    }
+                }
             } else
             for (int g = 0; g < ft.n_groups; ++g) {
                 const int n4 = s_meta[g];
@@ -868,18 +889,18 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     }
 }
 
-template <int NW, bool PIP, bool PREF, int UNR = 0, bool TM = false>
+template <int NW, bool PIP, bool PREF, bool TM = false, int UNR = 0>
 static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                   int num_sms, cudaStream_t stream) {
     const int smem = fast_layout(ft, NW, PREF, TM).total * 4;
-    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP, PREF, UNR, TM>,
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP, PREF, TM, UNR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long frames = (long long)a.B * a.T;
     if (frames <= 0) return cudaSuccess;
     long long grid = (frames + NW - 1) / NW;
     if (grid > num_sms) grid = num_sms;
-    frames_fast_2048<NW, PIP, PREF, UNR, TM><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    frames_fast_2048<NW, PIP, PREF, TM, UNR><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
@@ -890,15 +911,18 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
     constexpr int kMaxSmem = 227 * 1024;
     // default window: 16 warps with the next frame's copy in flight (Hann synthesised in registers)
     static const bool no_pref = [] { const char* e = getenv("HLMC_NO_PREF"); return e && e[0] == '1'; }();
-    // the default plan (128 mels, step counts 3 / 3 / 7 / 14): mel gather with compile-time trip counts
-    static const bool no_unr = [] { const char* e = getenv("HLMC_NO_UNROLL"); return e && e[0] == '1'; }();
+    // per-lane tables in Tensor Memory (any window: it is one of the tables), next frame's copy in flight
     static const bool no_tm = [] { const char* e = getenv("HLMC_NO_TMEM"); return e && e[0] == '1'; }();
-    if (!no_pref && !no_tm && !pip && ft.tmem_tab != nullptr && ft.mel_unr == kMelUnrDefault && a.n_mels == 128 &&
-        a.mel_out != nullptr)
-        return launch_fast_nw<16, false, true, kMelUnrDefault, true>(a, d_tables, ft, num_sms, stream);
-    if (!no_pref && !no_unr && !pip && ft.hann && ft.mel_unr == kMelUnrDefault && a.n_mels == 128 &&
-        fast_layout(ft, 16, true).total * 4 <= kMaxSmem)
-        return launch_fast_nw<16, false, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream);
+    if (!no_pref && !no_tm && ft.tmem_tab != nullptr && fast_layout(ft, 16, true, true).total * 4 <= kMaxSmem) {
+        const bool dflt = ft.n_groups == 4 && a.n_mels == 128 &&
+                          (ft.mel_steps[0] | (ft.mel_steps[1] << 8) | (ft.mel_steps[2] << 16) | (ft.mel_steps[3] << 24)) == kMelUnrDefault;
+        if (dflt)
+            return pip ? launch_fast_nw<16, true, true, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream)
+                       : launch_fast_nw<16, false, true, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream);
+    }
+    if (!no_pref && !no_tm && ft.tmem_tab != nullptr && fast_layout(ft, 16, true, true).total * 4 <= kMaxSmem)
+        return pip ? launch_fast_nw<16, true, true, true>(a, d_tables, ft, num_sms, stream)
+                   : launch_fast_nw<16, false, true, true>(a, d_tables, ft, num_sms, stream);
     if (!no_pref && ft.hann && fast_layout(ft, 16, true).total * 4 <= kMaxSmem)
         return pip ? launch_fast_nw<16, true, true>(a, d_tables, ft, num_sms, stream)
                    : launch_fast_nw<16, false, true>(a, d_tables, ft, num_sms, stream);
