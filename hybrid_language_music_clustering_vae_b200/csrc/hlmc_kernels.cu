@@ -286,18 +286,19 @@ __device__ __forceinline__ void mel_steps_tm(int n4, uint32_t taddr, const float
 // The default plan (128 Slaney mels at 22.05 kHz: 3, 3, 7, 14 float4 steps for the four filter groups) gets its step
 // counts at compile time: every trip count and TMEM column is an immediate (measured: 3.80 against 4.03 ms).
 constexpr int kMelUnrDefault = 3 | (3 << 8) | (7 << 16) | (14 << 24);
-template <int UNR, int G, int CHMAX = 4>
+template <int UNR, int G>
 __device__ __forceinline__ float mel_group_tm(uint32_t tq, const float* __restrict__ pp) {
     constexpr int STEPS = (UNR >> (8 * G)) & 255;
     constexpr int COL = kTmMel + 4 * ((G > 0 ? (UNR & 255) : 0) + (G > 1 ? ((UNR >> 8) & 255) : 0) + (G > 2 ? ((UNR >> 16) & 255) : 0));
     float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
-    // chunks of CHMAX steps (4: one tcgen05.ld.x16; 2 where registers are short), then the tail in chunks of 2 and 1
-    constexpr int NC = STEPS / CHMAX;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) mel_chunk_tm<CHMAX>(tq + COL + 4 * CHMAX * c, pp + 4 * CHMAX * c, a01, a23);
-    constexpr int R0 = NC * CHMAX, REM = STEPS - R0;
-    if constexpr (REM >= 2) mel_chunk_tm<2>(tq + COL + 4 * R0, pp + 4 * R0, a01, a23);
-    if constexpr (REM & 1) mel_chunk_tm<1>(tq + COL + 4 * (R0 + (REM & 2)), pp + 4 * (R0 + (REM & 2)), a01, a23);
+    for (int c = 0; c < STEPS / 4; ++c) mel_chunk_tm<4>(tq + COL + 16 * c, pp + 16 * c, a01, a23);
+    if constexpr ((STEPS & 3) == 3) {
+        mel_chunk_tm<2>(tq + COL + 16 * (STEPS / 4), pp + 16 * (STEPS / 4), a01, a23);
+        mel_chunk_tm<1>(tq + COL + 16 * (STEPS / 4) + 8, pp + 16 * (STEPS / 4) + 8, a01, a23);
+    }
+    if constexpr ((STEPS & 3) == 2) mel_chunk_tm<2>(tq + COL + 16 * (STEPS / 4), pp + 16 * (STEPS / 4), a01, a23);
+    if constexpr ((STEPS & 3) == 1) mel_chunk_tm<1>(tq + COL + 16 * (STEPS / 4), pp + 16 * (STEPS / 4), a01, a23);
     a01 = __fadd2_rn(a01, a23);
     return a01.x + a01.y;
 }
@@ -337,28 +338,6 @@ __device__ __forceinline__ int issue_frame_tma(const FrameArgs& a, const WarpSta
     return shift;
 }
 
-// (callers without register-resident samples)
-template <bool PREF, bool TM = false>
-__device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
-                                               const float* nclip, int nt,
-                                               float2 (&P)[16], float2 (&S)[16], float& p512, float& s512,
-                                               float& ss, int& zc, float& m0l, float& m1l, float& m2l,
-                                               float& m0h, float& m1h, float& m2h);
-
-// DIRECT kernels: frame t of `clip` straight into registers (32 coalesced 8-byte loads per lane, all in flight) if the
-// frame holds no padding and starts 8-byte aligned; false = build it by hand.
-template <int XN>
-__device__ __forceinline__ bool issue_frame_ldg(const FrameArgs& a, const float* clip, int t, int lane, float2 (&xr)[XN]) {
-    const int fs = t * a.hop - a.pad;
-    const bool interior = (fs >= 0) && (fs + kFastNfft <= a.n);
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(clip + fs);
-    if (XN != 32 || !interior || (addr & 7)) return false;
-    const float2* p = reinterpret_cast<const float2*>(addr) + lane;
-#pragma unroll
-    for (int j = 0; j < XN; ++j) xr[j] = __ldg(p + 32 * j);
-    return true;
-}
-
 // One frame, from samples to spectrum, shared by the feature kernel and the chroma kernel.
 // On return P[i] / S[i] hold |X|^2 / |X| of bin 16*lane + i (.x, the lane's low run) and of bin
 // 1024 - 16*lane - i (.y, its mirrored high run); p512 / s512 are bin 512; ss = sum of squares of
@@ -372,18 +351,12 @@ __device__ __forceinline__ bool issue_frame_ldg(const FrameArgs& a, const float*
 // frees pay for (2) a landing zone of its own, so the TMA copy of the warp's NEXT frame (nclip, nt) is
 // started as soon as the transposes are done and flies while the statistics and the mel projection of
 // this frame run - the wait at the top of the next frame is then (nearly) free.
-// DIRECT (TM kernels): no TMA staging at all.  The frame's 2048 samples are already in registers - xr[j] = samples
-// 2(lane+32j), 2(lane+32j)+1, loaded straight from global memory by issue_frame_ldg() while the previous frame's mel
-// gather ran (w.pending) - so the 8 KB per frame neither land in shared memory nor are read back from it; frames
-// with padding or an odd alignment are built by hand through the warp buffer as before.
-template <bool PREF, bool TM, bool DIRECT, int XN>
+template <bool PREF, bool TM = false>
 __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
                                                const float* nclip, int nt,
                                                float2 (&P)[16], float2 (&S)[16], float& p512, float& s512,
                                                float& ss, int& zc, float& m0l, float& m1l, float& m2l,
-                                               float& m0h, float& m1h, float& m2h, float2 (&xr_)[XN]) {
-    static_assert(XN == (DIRECT ? 32 : 1), "xr: the frame's samples in registers (DIRECT) or a dummy");
-    static_assert(!DIRECT || TM, "DIRECT kernels read their tables from Tensor Memory");
+                                               float& m0h, float& m1h, float& m2h) {
     float* const sc = w.sc;
     float2* const sc2 = w.sc2;
     uint64_t* const mbar = w.mbar;
@@ -398,17 +371,13 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     int zc_edge = -1;
     int off;
 
-    // ---- stage the frame's samples in this warp's buffer (DIRECT: straight into registers, 32 loads in flight)
-    if constexpr (DIRECT) off = (w.pending || issue_frame_ldg(a, clip, t, lane, xr_)) ? 0 : -1;   // pending: loaded during the last frame's mel gather
-    else if (!PREF || !w.pending) off = issue_frame_tma(a, w, land, clip, t);
+    // ---- stage the frame's samples in this warp's buffer
+    if (!PREF || !w.pending) off = issue_frame_tma(a, w, land, clip, t);
     else off = w.pend_off;
-    const bool in_regs = DIRECT && off >= 0;
     w.pending = false;
     if (off >= 0) {
-        if constexpr (!DIRECT) {
-            mbar_wait(mbar, parity);
-            parity ^= 1u;
-        }
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
     } else {
         // edge frame (or odd alignment): build the padded frame by hand; ZCR pads with "edge"
         int zc = 0;
@@ -435,11 +404,6 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
         zc_edge = zc;
         off = 0;
         __syncwarp();
-        if constexpr (DIRECT) {              // hand-built frame: from the warp buffer into the same registers
-            const float2* xq = reinterpret_cast<const float2*>(land);
-#pragma unroll
-            for (int j = 0; j < XN; ++j) xr_[j] = xq[lane + 32 * j];
-        }
     }
 
     unsigned za = 0u, zb = 0u;
@@ -451,17 +415,13 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
         const float2* xp = reinterpret_cast<const float2*>(land + off);
         const float2 zt = make_float2(zthr, zthr);
         float2 ss2 = make_float2(0.0f, 0.0f);
-        (void)in_regs;
 #pragma unroll
         for (int jc = 0; jc < 4; ++jc) {
             uint32_t wr[16];
             tmem_ld16_issue(w.tq + kTmWin + 16 * jc, wr);
             float2 x[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if constexpr (DIRECT) x[u] = xr_[DIRECT ? 8 * jc + u : 0];
-                else x[u] = xp[lane + 32 * (8 * jc + u)];
-            }
+            for (int u = 0; u < 8; ++u) x[u] = xp[lane + 32 * (8 * jc + u)];
             tmem_wait16(wr);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -573,7 +533,7 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     __syncwarp();
 
     // ---- the landing zone is free again: start the copy of this warp's next frame
-    if (PREF && !DIRECT && nclip != nullptr) {
+    if (PREF && nclip != nullptr) {
         const int sh = issue_frame_tma(a, w, land, nclip, nt);
         w.pending = sh >= 0;
         w.pend_off = sh;
@@ -616,21 +576,11 @@ __device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w,
     p512 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);
     s512 = fast_sqrt(p512);
 }
-template <bool PREF, bool TM>
-__device__ __forceinline__ void frame_spectrum(const FrameArgs& a, WarpState& w, const float* clip, int t,
-                                               const float* nclip, int nt,
-                                               float2 (&P)[16], float2 (&S)[16], float& p512, float& s512,
-                                               float& ss, int& zc, float& m0l, float& m1l, float& m2l,
-                                               float& m0h, float& m1h, float& m2h) {
-    float2 none[1];
-    frame_spectrum<PREF, TM, false, 1>(a, w, clip, t, nclip, nt, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h, none);
-}
 
-template <int NW, bool PIP, bool PREF, bool TM = false, int UNR = 0, bool DIRECT = false>
+template <int NW, bool PIP, bool PREF, bool TM = false, int UNR = 0>
 __global__ void __launch_bounds__(NW * 32, 1)
 frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
-    static_assert(!TM || PREF || DIRECT, "TM kernels: a landing zone of its own, or no landing zone at all");
-    static_assert(!DIRECT || (TM && !PREF), "DIRECT kernels: tables in Tensor Memory, one buffer per warp");
+    static_assert(!TM || PREF, "TM kernels use the layout with a landing zone of its own");
     static_assert(UNR == 0 || TM, "compile-time mel step counts: TM kernels only");
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = NW * 32;
@@ -706,18 +656,16 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     w.zhi_base = 17 * (63 - lane) + 16;          // read:  k = 1024-16*lane-i (i>=1) -> zhi_base - i
     w.zhi0 = (lane == 0) ? 0 : 17 * (64 - lane); // read:  k = (1024-16*lane) mod 1024
 
-    float2 xr[DIRECT ? 32 : 1];
     for (long long g = g0; g < g1; g += NW) {
         const float* clip = a.wave + (long long)b * a.pitch;
-
         // this warp's next frame (PREF kernels start its copy half-way through this one)
         int nb = b, nt = t + NW;
         while (nt >= a.T) { nt -= a.T; ++nb; }
-        const float* nclip = ((PREF || DIRECT) && g + NW < g1) ? a.wave + (long long)nb * a.pitch : nullptr;
+        const float* nclip = (PREF && g + NW < g1) ? a.wave + (long long)nb * a.pitch : nullptr;
         float2 P[16], S[16];
         float p512, s512, ss, m0l, m1l, m2l, m0h, m1h, m2h;
         int zc;
-        frame_spectrum<PREF, TM, DIRECT>(a, w, clip, t, nclip, nt, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h, xr);
+        frame_spectrum<PREF, TM>(a, w, clip, t, nclip, nt, P, S, p512, s512, ss, zc, m0l, m1l, m2l, m0h, m1h, m2h);
 
         // ---- chroma_stft: keep the power spectrum for the projection that follows the tuning estimate
         //      (8 coalesced 16-byte stores per lane, in the lane's register order: no second STFT pass)
@@ -858,9 +806,6 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             if (lane == 0) a.cand_count[(size_t)b * a.T + t] = min(base, a.cand_cap);
         }
 
-        // ---- DIRECT: the next frame's samples start their way into registers; they land during the mel gather
-        if constexpr (DIRECT) { if (nclip != nullptr) w.pending = issue_frame_ldg(a, nclip, nt, lane, xr); }
-
         // ---- phase 8: banded mel projection (librosa.feature.melspectrogram's einsum);
         //      start offsets were shifted on the host so that the 32 lanes hit 32 banks
         if (a.mel_out != nullptr) {
@@ -871,11 +816,10 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             if constexpr (TM && UNR != 0) {
                 uint32_t st4[4];
                 tmem_ld4(w.tq + kTmMeta, st4);       // the lane's first tap in each group
-                constexpr int CHM = DIRECT ? 2 : 4;      // DIRECT: 64 registers hold the next frame's samples meanwhile
-                const float acc0 = mel_group_tm<UNR, 0, CHM>(w.tq, sc + st4[0]);
-                const float acc1 = mel_group_tm<UNR, 1, CHM>(w.tq, sc + st4[1]);
-                const float acc2 = mel_group_tm<UNR, 2, CHM>(w.tq, sc + st4[2]);
-                const float acc3 = mel_group_tm<UNR, 3, CHM>(w.tq, sc + st4[3]);
+                const float acc0 = mel_group_tm<UNR, 0>(w.tq, sc + st4[0]);
+                const float acc1 = mel_group_tm<UNR, 1>(w.tq, sc + st4[1]);
+                const float acc2 = mel_group_tm<UNR, 2>(w.tq, sc + st4[2]);
+                const float acc3 = mel_group_tm<UNR, 3>(w.tq, sc + st4[3]);
                 outb[(size_t)lane * mstride] = acc0;
                 outb[(size_t)(32 + lane) * mstride] = acc1;
                 outb[(size_t)(64 + lane) * mstride] = acc2;
@@ -945,18 +889,18 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     }
 }
 
-template <int NW, bool PIP, bool PREF, bool TM = false, int UNR = 0, bool DIRECT = false>
+template <int NW, bool PIP, bool PREF, bool TM = false, int UNR = 0>
 static cudaError_t launch_fast_nw(const FrameArgs& a, const float* d_tables, const FastTables& ft,
                                   int num_sms, cudaStream_t stream) {
     const int smem = fast_layout(ft, NW, PREF, TM).total * 4;
-    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP, PREF, TM, UNR, DIRECT>,
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_2048<NW, PIP, PREF, TM, UNR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long frames = (long long)a.B * a.T;
     if (frames <= 0) return cudaSuccess;
     long long grid = (frames + NW - 1) / NW;
     if (grid > num_sms) grid = num_sms;
-    frames_fast_2048<NW, PIP, PREF, TM, UNR, DIRECT><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    frames_fast_2048<NW, PIP, PREF, TM, UNR><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
@@ -972,9 +916,6 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
     if (!no_pref && !no_tm && ft.tmem_tab != nullptr && fast_layout(ft, 16, true, true).total * 4 <= kMaxSmem) {
         const bool dflt = ft.n_groups == 4 && a.n_mels == 128 &&
                           (ft.mel_steps[0] | (ft.mel_steps[1] << 8) | (ft.mel_steps[2] << 16) | (ft.mel_steps[3] << 24)) == kMelUnrDefault;
-        static const bool no_direct = [] { const char* e = getenv("HLMC_NO_DIRECT"); return e && e[0] == '1'; }();
-        if (dflt && !pip && !no_direct)
-            return launch_fast_nw<16, false, false, true, kMelUnrDefault, true>(a, d_tables, ft, num_sms, stream);
         if (dflt)
             return pip ? launch_fast_nw<16, true, true, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream)
                        : launch_fast_nw<16, false, true, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream);
