@@ -569,7 +569,8 @@ def main():
     pipes, pipes_note = load_capture("frames_fast_pipes.json")
     step_ms = ms / args.steps
     roofline = {
-        "bound": "fp32", "kernel": "frames_fast_2048", "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "frames_fast_2048<16 warps, TM> (per-lane tables in Tensor Memory, tcgen05.ld)",
+        "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": k1_tflops / fp32_peak,
         "peak_source": "FP32 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has no fp32 entry; "
                        "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",

@@ -53,7 +53,9 @@ import importlib.util
 _spec = importlib.util.spec_from_file_location("bench_for_hash", os.path.join(ROOT, "bench.py"))
 _bench = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_bench)
-SOURCE_HASH = _bench.kernel_source_hash()      # bench.py quotes a capture only when this matches the built sources
+SOURCE_HASH = _bench.kernel_source_hash()
+# the shipped default-plan kernel: frames_fast_2048<16, false, true, /*TM*/true, kMelUnrDefault>
+KSUB = "frames_fast_2048ILi16ELb0ELb1ELb1ELi235340547E"      # bench.py quotes a capture only when this matches the built sources
 
 def unit_scale(u):
     return {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
@@ -104,14 +106,14 @@ subprocess.run(f"cd {tmp} && rm -f *.cubin && cuobjdump -xelf all {lib} > /dev/n
                f"nvdisasm --print-line-info -c hlmc_kernels.sm_100a.cubin > k.dis 2>/dev/null", shell=True, check=True)
 frames = clips * 130
 res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_by_line.py"), src_csv, f"{tmp}/k.dis",
-                      "frames_fast_2048ILi16ELb0ELb1E", str(frames), "80"], capture_output=True, text=True)
+                      KSUB, str(frames), "80"], capture_output=True, text=True)
 with open(os.path.join(out_dir, f"{tag}_frames_fast_by_line.txt"), "w") as f:
     f.write("# executed warp-instructions, share of stall samples and shared-memory wavefronts per frame,\n"
             "# by CUDA source line (ncu source page joined with nvdisasm line info)\n" + res.stdout + res.stderr[-2000:])
 # SASS listing of the frames kernel
 sass = subprocess.run(f"cuobjdump -sass {lib}", shell=True, capture_output=True, text=True).stdout
 chunks = sass.split("\tFunction : ")
-pick = [c for c in chunks if c.startswith("_ZN4hlmc16frames_fast_2048ILi16ELb0ELb1E")] + [c for c in chunks if c.startswith("_ZN4hlmc6db_dctILi40")]
+pick = [c for c in chunks if c.startswith("_ZN4hlmc16" + KSUB)] + [c for c in chunks if c.startswith("_ZN4hlmc6db_dctILi40")]
 with gzip.open(os.path.join(out_dir, f"{tag}_sass_frames_fast_db_dct.txt.gz"), "wt") as f:
     f.write("\n\tFunction : ".join(pick))
 mix = {}
@@ -130,11 +132,12 @@ with open(os.path.join(out_dir, f"{tag}_sass_mix_frames_fast.json"), "w") as f:
 # the Blackwell / TMA evidence lines of the frames kernel
 ev = []
 for line in pick[0].splitlines() if pick else []:
-    if any(op in line for op in ("UBLKCP", "SYNCS", "MUFU.SQRT", "FENCE.VIEW.ASYNC", "UTMA")):
+    if any(op in line for op in ("UBLKCP", "SYNCS", "MUFU.SQRT", "FENCE.VIEW.ASYNC", "UTMA", "LDTM", "STTM", "UTCATOMSWS")):
         ev.append(line.rstrip())
 packed = {op: [l.rstrip() for l in (pick[0].splitlines() if pick else []) if f" {op} " in l] for op in ("FFMA2", "FADD2", "FMUL2")}
 with open(os.path.join(out_dir, f"{tag}_sass_evidence.txt"), "w") as f:
-    f.write("# frames_fast_2048<16,*>: TMA bulk copy (UBLKCP), mbarrier (SYNCS), async-proxy fence, MUFU lines\n")
+    f.write("# frames_fast_2048<16,0,1,TM,default steps>: TMA bulk copy (UBLKCP), mbarrier (SYNCS), async-proxy fence, MUFU lines,\n"
+            "# Tensor Memory: allocation (UTCATOMSWS), table fill (STTM), table reads (LDTM = tcgen05.ld)\n")
     f.write("\n".join(ev) + "\n")
     f.write("# Blackwell packed FP32 (sm_100 only): " + ", ".join(f"{op} x{len(v)}" for op, v in packed.items()) +
             " static instructions; first lines of each (operand swizzles .LO_HI / sign patterns .NP fold the +-i rotations):\n")
