@@ -179,6 +179,11 @@ class FeatureExtractor:
     def force_generic(self, flag: bool = True):
         _check(lib.hlmc_plan_set_path(self._plan, int(bool(flag))))
 
+    def set_path(self, path: int):
+        """0 = automatic, 1 = shared-memory FFT kernel (HLMC_PATH_GENERIC), 2 = register-FFT kernel with its tables
+        in shared memory instead of Tensor Memory (HLMC_PATH_FAST_SMEM_TABLES); tests cross-check the three."""
+        _check(lib.hlmc_plan_set_path(self._plan, int(path)))
+
     def set_timing(self, enable: bool):
         _check(lib.hlmc_plan_set_timing(self._plan, int(bool(enable))))
 

@@ -53,7 +53,7 @@ struct ResampleTaps {
 struct hlmc_plan {
     hlmc_params p;
     int device = 0, num_sms = 0, F = 0;
-    int force_generic = 0;
+    int force_generic = 0, no_tmem = 0;
     bool fast_ok = false;
     std::vector<float> mel_dense, dct;           // host copies
     int ncp = 0;
@@ -734,7 +734,8 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
 
 int hlmc_plan_set_path(hlmc_plan* plan, int generic) {
     if (!plan) return fail(HLMC_ERR_PARAM, "null plan");
-    plan->force_generic = generic ? 1 : 0;
+    plan->force_generic = (generic == HLMC_PATH_GENERIC) ? 1 : 0;
+    plan->no_tmem = (generic == HLMC_PATH_FAST_SMEM_TABLES) ? 1 : 0;
     return HLMC_OK;
 }
 int hlmc_plan_uses_fast_path(const hlmc_plan* plan) {
@@ -760,6 +761,7 @@ static FrameArgs make_frame_args(const hlmc_plan* pl, const float* d_wave, int64
     a.binhz = float(double(pl->p.sr) / double(pl->p.n_fft));
     a.roll_percent = pl->p.roll_percent; a.zcr_thr = pl->p.zcr_threshold;
     a.pip_klo = pl->pip_klo; a.pip_khi = pl->pip_khi; a.pip_threshold = 0.1f;
+    a.no_tmem = pl->no_tmem;
     return a;
 }
 

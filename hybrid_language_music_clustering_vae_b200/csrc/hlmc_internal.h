@@ -76,6 +76,7 @@ struct FrameArgs {
     // power-spectrum stash for the chroma projection (register-FFT kernel with piptrack only) or NULL:
     // (B, T, kStashFloats), each lane's 32 bins in its register order [lane][32], then bin 512
     float* pstash;
+    int no_tmem;            // 1: keep the n_fft 2048 kernel's tables in shared memory (hlmc_plan_set_path, tests)
 };
 constexpr int kStashFloats = 32 * 32 + 4;
 

@@ -913,14 +913,15 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
     static const bool no_pref = [] { const char* e = getenv("HLMC_NO_PREF"); return e && e[0] == '1'; }();
     // per-lane tables in Tensor Memory (any window: it is one of the tables), next frame's copy in flight
     static const bool no_tm = [] { const char* e = getenv("HLMC_NO_TMEM"); return e && e[0] == '1'; }();
-    if (!no_pref && !no_tm && ft.tmem_tab != nullptr && fast_layout(ft, 16, true, true).total * 4 <= kMaxSmem) {
+    const bool use_tm = !no_pref && !no_tm && !a.no_tmem && ft.tmem_tab != nullptr && fast_layout(ft, 16, true, true).total * 4 <= kMaxSmem;
+    if (use_tm) {
         const bool dflt = ft.n_groups == 4 && a.n_mels == 128 &&
                           (ft.mel_steps[0] | (ft.mel_steps[1] << 8) | (ft.mel_steps[2] << 16) | (ft.mel_steps[3] << 24)) == kMelUnrDefault;
         if (dflt)
             return pip ? launch_fast_nw<16, true, true, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream)
                        : launch_fast_nw<16, false, true, true, kMelUnrDefault>(a, d_tables, ft, num_sms, stream);
     }
-    if (!no_pref && !no_tm && ft.tmem_tab != nullptr && fast_layout(ft, 16, true, true).total * 4 <= kMaxSmem)
+    if (use_tm)
         return pip ? launch_fast_nw<16, true, true, true>(a, d_tables, ft, num_sms, stream)
                    : launch_fast_nw<16, false, true, true>(a, d_tables, ft, num_sms, stream);
     if (!no_pref && ft.hann && fast_layout(ft, 16, true).total * 4 <= kMaxSmem)

@@ -110,10 +110,16 @@ int  hlmc_plan_create(const hlmc_params *params, const double *window,
                       const float *mel_basis, int device, hlmc_plan **out);
 void hlmc_plan_destroy(hlmc_plan *plan);
 /* Kernel selection.  n_fft == 2048 (the only size the reference uses) runs the
- * register-FFT kernel; other power-of-two sizes run the shared-memory FFT
- * kernel.  generic != 0 forces the latter (tests cross-check the two); the
- * environment variable HLMC_FORCE_GENERIC=1 does the same at plan creation.  */
-int  hlmc_plan_set_path(hlmc_plan *plan, int generic);
+ * register-FFT kernel with its per-lane tables (window, twiddles, mel weights)
+ * in Tensor Memory; n_fft 4096 / 1024 / 512 have register-FFT kernels of their
+ * own; other power-of-two sizes run the shared-memory FFT kernel.
+ * HLMC_PATH_GENERIC forces the latter, HLMC_PATH_FAST_SMEM_TABLES keeps the
+ * n_fft 2048 tables in shared memory (tests cross-check the three); the
+ * environment variables HLMC_FORCE_GENERIC=1 / HLMC_NO_TMEM=1 do the same.   */
+#define HLMC_PATH_AUTO 0
+#define HLMC_PATH_GENERIC 1
+#define HLMC_PATH_FAST_SMEM_TABLES 2
+int  hlmc_plan_set_path(hlmc_plan *plan, int path);
 int  hlmc_plan_uses_fast_path(const hlmc_plan *plan);
 /* Copy of the filterbank / DCT the plan uses (for inspection and tests).     */
 int  hlmc_plan_mel_basis(const hlmc_plan *plan, float *h_out /* n_mels*(1+n_fft/2) */);

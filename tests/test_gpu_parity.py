@@ -614,3 +614,41 @@ def test_random_parameter_combinations(built, n, pitch_extra, kw):
     lengths and row pitches (mis-aligned rows take the hand-built staging path)."""
     y = built.synth.synth_batch(5, n, seed=n)
     _check_batch(built, y, pitch=n + pitch_extra, **kw)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(window="hamming"), dict(n_mels=40, n_mfcc=13), dict(n_mels=64, htk=True),
+                                dict(n_mels=256), dict(pad_mode="reflect", power=1.0), dict(win_length=1024)])
+def test_tensor_memory_tables_match_shared_memory_tables(built, kw):
+    """The n_fft = 2048 kernel reads its per-lane tables (window, twiddles, banded mel weights, gather offsets) from
+    Tensor Memory (tcgen05.ld); HLMC_PATH_FAST_SMEM_TABLES runs the same pipeline with the tables in shared memory.
+    The two differ only in how table values are rounded (the shared-memory variant synthesises the Hann window and
+    rotates one split twiddle per lane in registers, the TMEM variant reads values rounded once from float64), i.e.
+    they are two float32 FFTs that each meet the oracle tolerances; against each other they are held to the same."""
+    import torch
+
+    hl = built
+    y = np.concatenate([hl.synth.synth_batch(24, 30011, seed=77), np.zeros((1, 30011), np.float32)])   # odd length: edge frames too
+    yd = torch.from_numpy(y).cuda()
+    ex = hl.FeatureExtractor(n_mfcc=kw.get("n_mfcc", 20), ref=np.max, **{k: v for k, v in kw.items() if k != "n_mfcc"})
+    a = {k: v.clone() for k, v in ex.extract_device(yd).items()}
+    ex.set_path(2)
+    b = ex.extract_device(yd)
+    assert (a["logmel"] - b["logmel"]).abs().max().item() <= LOGMEL_TOL_DB
+    for k in ("mfcc", "stats"):
+        for c in range(a[k].shape[0]):
+            d = (a[k][c] - b[k][c]).abs().amax(dim=-1)
+            if k == "mfcc":             # 1e-4 of the clip's largest coefficient, as against the oracle
+                assert d.max().item() <= REL_TOL * max(b[k][c].abs().max().item(), 1e-6), (k, c, d.tolist())
+            else:                       # per statistic; rolloff (row 2) may flip by one bin at a tie; zcr (row 3) is exact
+                assert torch.equal(a[k][c][3], b[k][c][3])
+                scale = b[k][c].abs().amax(dim=-1).clamp_min(1e-6)
+                keep = torch.tensor([0, 1, 4], device=d.device)
+                assert (d[keep] <= REL_TOL * scale[keep]).all(), (k, c, d.tolist(), scale.tolist())
+    # the chroma variant (piptrack epilogue + power-spectrum stash) on both table paths
+    if not kw:
+        ex.set_path(0)
+        ca = {k: v.clone() for k, v in ex.extract_device(yd, chroma=True).items()}
+        ex.set_path(2)
+        cb = ex.extract_device(yd, chroma=True)
+        assert torch.equal(ca["tuning"], cb["tuning"])
+        assert (ca["chroma"] - cb["chroma"]).abs().max().item() <= 1e-5
