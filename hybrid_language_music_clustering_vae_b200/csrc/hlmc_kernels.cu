@@ -617,12 +617,23 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;");
         tbase = *s_taddr;
-        if (warp < 4) {
+        {
+            // quarter warp%4 is filled by its NW/4 warps, each a contiguous share of the columns, 4 loads in flight
+            static_assert(NW % 4 == 0, "a whole number of warps per TMEM quarter");
             const float4* src = reinterpret_cast<const float4*>(ft.tmem_tab + (size_t)lane * ft.tmem_cols);
-            for (int c = 0; c < ft.tmem_cols; c += 4) {
-                const float4 q = __ldg(src + c / 4);
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tbase + ((uint32_t)(32 * warp) << 16) + c),
-                             "r"(__float_as_uint(q.x)), "r"(__float_as_uint(q.y)), "r"(__float_as_uint(q.z)), "r"(__float_as_uint(q.w)));
+            const int n4 = ft.tmem_cols / 4, per = (n4 + NW / 4 - 1) / (NW / 4);
+            const int c0 = (warp >> 2) * per, c1 = min(n4, c0 + per);
+            const uint32_t tqw = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+            for (int c = c0; c < c1; c += 4) {
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = (c + u < c1) ? __ldg(src + c + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c + u < c1)
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tqw + 4 * (c + u)),
+                                     "r"(__float_as_uint(q[u].x)), "r"(__float_as_uint(q[u].y)), "r"(__float_as_uint(q[u].z)),
+                                     "r"(__float_as_uint(q[u].w)));
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
