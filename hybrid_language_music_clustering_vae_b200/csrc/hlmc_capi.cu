@@ -723,9 +723,45 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
             }
         memcpy(&blob[ft.mel_meta], meta.data(), meta.size() * 4);
         if (!melw.empty()) memcpy(&blob[ft.mel_w], melw.data(), melw.size() * 4);
+        for (int r = 0; r < R && r < 32; ++r) ft.mel_steps[r] = meta[r];
         pl->ft = ft;
         UP(d_fast, blob)
         pl->fast_ok = sub_smem_bytes(ft, 16, Lg) <= 227 * 1024;
+        {   // the same tables per lane for Tensor Memory (frames_sub<..., TM>), see kSub* in hlmc_internal.h
+            int total_steps = 0;
+            for (int r = 0; r < R; ++r) total_steps += meta[r];
+            const int cols = kSubMel + 4 * total_steps;
+            if (R <= 32 && cols <= kTmAlloc) {
+                std::vector<float> tm((size_t)32 * cols, 0.0f);
+                for (int l = 0; l < 32; ++l) {
+                    const int lg = l & (Lg - 1);
+                    float* row = &tm[(size_t)l * cols];
+                    for (int j = 0; j < 32; ++j) {
+                        row[kSubWin + 2 * j] = win[2 * (lg + Lg * j)];
+                        row[kSubWin + 2 * j + 1] = win[2 * (lg + Lg * j) + 1];
+                    }
+                    for (int k1 = 1; k1 < 32; ++k1) {
+                        row[kSubTw1 + 2 * (k1 - 1)] = blob[ft.tw1 + ((k1 - 1) * Lg + lg) * 2];
+                        row[kSubTw1 + 2 * (k1 - 1) + 1] = blob[ft.tw1 + ((k1 - 1) * Lg + lg) * 2 + 1];
+                    }
+                    for (int i = 0; i < 16; ++i) {
+                        row[kSubTw2 + 2 * i] = blob[ft.tw2 + (i * Lg + lg) * 2];
+                        row[kSubTw2 + 2 * i + 1] = blob[ft.tw2 + (i * Lg + lg) * 2 + 1];
+                    }
+                    int pre = 0;
+                    for (int r = 0; r < R; ++r) {
+                        memcpy(&row[kSubMeta + r], &meta[2 * R + r * Lg + lg], 4);
+                        for (int st = 0; st < meta[r]; ++st)
+                            for (int c = 0; c < 4; ++c)
+                                row[kSubMel + 4 * (pre + st) + c] = melw[(size_t)meta[R + r] + ((size_t)st * Lg + lg) * 4 + c];
+                        pre += meta[r];
+                    }
+                }
+                UP(d_tmem_tab, tm)
+                pl->ft.tmem_tab = pl->d_tmem_tab;
+                pl->ft.tmem_cols = cols;
+            }
+        }
     }
 #undef UP
     *out = pl;

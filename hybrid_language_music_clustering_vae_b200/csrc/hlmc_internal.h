@@ -24,7 +24,7 @@ struct FastTables {
     int hann;       // 1: the window is the full-length periodic Hann (n_fft 2048: synthesised in registers)
     int hann_cs;    // 32 float4: (cos, cos', sin, sin') of 2*pi*(2*lane + {0,1}) / n_fft
     int nowin;      // floats before the window (multiple of 4)
-    int mel_steps[kMaxMelGroups];   // float4 steps per filter group (TM kernels read them from the kernel parameters)
+    int mel_steps[32];   // float4 steps per filter group / round (TM kernels read them from the kernel parameters)
     // per-lane tables for Tensor Memory (TM kernels; global memory, [32 lanes][tmem_cols] floats) or NULL
     const float* tmem_tab;
     int tmem_cols;  // multiple of 4, <= 512
@@ -49,6 +49,12 @@ constexpr int kTmTw2 = 128;     // 32: -i*W_2048^(16*lane + i), i = 0..15
 constexpr int kTmMeta = 160;    // 8: first tap of the lane's filter in each of the (up to 8) groups (int32 bits)
 constexpr int kTmMel = 168;     // banded mel weights, float4 per step, group after group
 constexpr int kTmAlloc = 512;   // columns allocated (all of TMEM: one CTA per SM)
+// ... and of frames_sub's (n_fft 1024 / 512; lane l reads the entries of lane-in-group l mod L)
+constexpr int kSubWin = 0;      // 64: 0.5*window[2(lg+L*j)], [..+1], j = 0..31
+constexpr int kSubTw1 = 64;     // 64: W_M^(lg*k1) as (cos, -sin), k1 = 1..31
+constexpr int kSubTw2 = 128;    // 32: -i*W_N^(16*lg + i), i = 0..15
+constexpr int kSubMeta = 160;   // 32: first tap of the lane's filter in each mel round (int32 bits)
+constexpr int kSubMel = 192;    // banded mel weights, float4 per step, round after round
 
 struct FrameArgs {
     const float* wave;      // (B, pitch)
@@ -128,7 +134,7 @@ cudaError_t launch_frames_fast4096(const FrameArgs& a, const float* d_tables, co
 int fast4_smem_bytes(const Fast4Tables& ft);
 cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
                               cudaStream_t stream);
-int sub_smem_bytes(const FastTables& ft, int nwarps, int L);
+int sub_smem_bytes(const FastTables& ft, int nwarps, int L, bool tm = false);
 cudaError_t launch_chroma_fast(const FrameArgs& a, const ChromaArgs& c, const float* d_tables,
                                const FastTables& ft, int num_sms, cudaStream_t stream);
 cudaError_t launch_chroma_project(const float* pstash, const ChromaArgs& c, long long B, int T, int num_sms,

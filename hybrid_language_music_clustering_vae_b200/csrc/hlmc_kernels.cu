@@ -207,6 +207,47 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
 }
 __device__ __forceinline__ float2 f2_of(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
+// CTA-wide: allocate the SM's Tensor Memory (all 512 columns: one CTA per SM), fill the four 32-lane quarters with
+// the per-lane tables ft.tmem_tab [32][ft.tmem_cols] (quarter warp%4 by its NW/4 warps, each a contiguous share of
+// the columns, 4 loads in flight) and return the base address.  Ends with the fence half of a CTA barrier: the
+// caller's next __syncthreads() + tcgen05.fence::after_thread_sync publishes the tables.
+template <int NW>
+__device__ __forceinline__ uint32_t tmem_tables_setup(const FastTables& ft, uint32_t* s_taddr, int warp, int lane) {
+    static_assert(NW % 4 == 0, "a whole number of warps per TMEM quarter");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_taddr)), "r"(kTmAlloc));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tbase = *s_taddr;
+    const float4* src = reinterpret_cast<const float4*>(ft.tmem_tab + (size_t)lane * ft.tmem_cols);
+    const int n4 = ft.tmem_cols / 4, per = (n4 + NW / 4 - 1) / (NW / 4);
+    const int c0 = (warp >> 2) * per, c1 = min(n4, c0 + per);
+    const uint32_t tqw = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    for (int c = c0; c < c1; c += 4) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = (c + u < c1) ? __ldg(src + c + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + u < c1)
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tqw + 4 * (c + u)),
+                             "r"(__float_as_uint(q[u].x)), "r"(__float_as_uint(q[u].y)), "r"(__float_as_uint(q[u].z)),
+                             "r"(__float_as_uint(q[u].w)));
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    return tbase;
+}
+// CTA-wide, at the end of the kernel (every warp must get here): free the Tensor Memory.
+__device__ __forceinline__ void tmem_tables_release(uint32_t tbase, int warp) {
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kTmAlloc));
+}
+
 // Banded mel gather of one (group, lane): n4 float4 steps of 4 taps each.  The step count is
 // warp-uniform but only known at run time.  Steps are taken in straight-line chunks of 4, 2 and 1 so
 // that all shared-memory loads of a chunk are in flight before its first multiply-add (a step-by-step
@@ -606,39 +647,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         fence_mbar_init();
     }
     uint32_t tbase = 0;
-    if constexpr (TM) {
-        // all of this SM's Tensor Memory; warp q fills lanes 32q..32q+31 with the per-lane tables
-        uint32_t* s_taddr = reinterpret_cast<uint32_t*>(smem + 2 * NW);
-        if (warp == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_taddr)), "r"(kTmAlloc));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        tbase = *s_taddr;
-        {
-            // quarter warp%4 is filled by its NW/4 warps, each a contiguous share of the columns, 4 loads in flight
-            static_assert(NW % 4 == 0, "a whole number of warps per TMEM quarter");
-            const float4* src = reinterpret_cast<const float4*>(ft.tmem_tab + (size_t)lane * ft.tmem_cols);
-            const int n4 = ft.tmem_cols / 4, per = (n4 + NW / 4 - 1) / (NW / 4);
-            const int c0 = (warp >> 2) * per, c1 = min(n4, c0 + per);
-            const uint32_t tqw = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
-            for (int c = c0; c < c1; c += 4) {
-                float4 q[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) q[u] = (c + u < c1) ? __ldg(src + c + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (c + u < c1)
-                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tqw + 4 * (c + u)),
-                                     "r"(__float_as_uint(q[u].x)), "r"(__float_as_uint(q[u].y)), "r"(__float_as_uint(q[u].z)),
-                                     "r"(__float_as_uint(q[u].w)));
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;");
-    }
+    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
     __syncthreads();
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
 
@@ -893,11 +902,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         t = nt; b = nb;
         __syncwarp();                       // scratch reads are done before the next frame lands
     }
-    if constexpr (TM) {
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kTmAlloc));
-    }
+    if constexpr (TM) tmem_tables_release(tbase, warp);
 }
 
 template <int NW, bool PIP, bool PREF, bool TM = false, int UNR = 0>
@@ -1370,12 +1375,14 @@ template <int L> __device__ __forceinline__ int group_sum_i(int v) {
     return v;
 }
 
-int sub_smem_bytes(const FastTables& ft, int nwarps, int L) {
+int sub_smem_bytes(const FastTables& ft, int nwarps, int L, bool tm) {
     const int wb = (L == 16) ? SubGeom<16>::WB : SubGeom<8>::WB;
-    return (((2 * nwarps + 3) & ~3) + ft.total + nwarps * wb) * 4;
+    return (((2 * nwarps + 3 + (tm ? 4 : 0)) & ~3) + (tm ? 0 : ft.total) + nwarps * wb) * 4;
 }
 
-template <int L, int NW, bool HANN>
+// TM: the per-lane tables (window, twiddles, mel weights and first taps) are read from Tensor Memory with tcgen05.ld
+// instead of shared memory, as in frames_fast_2048 (any window: HANN is then irrelevant and instantiated false).
+template <int L, int NW, bool HANN, bool TM = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTables ft) {
     using G = SubGeom<L>;
@@ -1384,22 +1391,27 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lg = lane & (L - 1), grp = lane / L, gbase = grp * L;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
-    float* tab = smem + ((2 * NW + 3) & ~3);
+    float* tab = smem + ((2 * NW + 3 + (TM ? 4 : 0)) & ~3);
+    const int tab_total = TM ? 0 : ft.total;          // TM: no table is staged in shared memory
     const float2* s_win = reinterpret_cast<const float2*>(tab + ft.win);
     const float2* s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + ft.tw2);
     const int* s_meta = reinterpret_cast<const int*>(tab + ft.mel_meta);
     const float* s_melw = tab + ft.mel_w;
-    float* wbuf = tab + ft.total + warp * G::WB;
+    float* wbuf = tab + tab_total + warp * G::WB;
     float* sc = wbuf + grp * G::GB;                   // this group's region
     float2* sc2 = reinterpret_cast<float2*>(sc);
     float* scp = sc + ((L == 8) ? 8 * (grp >> 1) : 0);   // power-spectrum scratch, skewed so groups hit different banks
 
-    for (int i = tid; i < ft.total / 4; i += NT)
+    for (int i = tid; i < tab_total / 4; i += NT)
         reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
-    for (int i = tid; i < NW * G::WB; i += NT) (tab + ft.total)[i] = 0.0f;
+    for (int i = tid; i < NW * G::WB; i += NT) (tab + tab_total)[i] = 0.0f;
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    uint32_t tbase = 0;
+    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
     __syncthreads();
+    if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tq = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
 
     // units of FW consecutive frames; a CTA owns a contiguous run of units, warps take them round-robin
     const int units_per_clip = (a.T + G::FW - 1) / G::FW;
@@ -1474,7 +1486,29 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
         float2 v[32];                                   // packed FP32: one complex value per register pair
         float ss;
         unsigned za = 0u, zb = 0u;
-        {
+        if constexpr (TM) {
+            const float2* xp = reinterpret_cast<const float2*>(sc + off);
+            const float2 zt = make_float2(zthr, zthr);
+            float2 ss2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int jc = 0; jc < 4; ++jc) {
+                uint32_t wr[16];
+                tmem_ld16_issue(tq + kSubWin + 16 * jc, wr);
+                float2 x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = xp[lg + L * (8 * jc + u)];
+                tmem_wait16(wr);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    ss2 = __ffma2_rn(x[u], x[u], ss2);
+                    const float2 xt = __fadd2_rn(x[u], zt);
+                    za = __funnelshift_l(__float_as_uint(xt.x), za, 1);
+                    zb = __funnelshift_l(__float_as_uint(xt.y), zb, 1);
+                    v[8 * jc + u] = __fmul2_rn(x[u], f2_of(wr[2 * u], wr[2 * u + 1]));
+                }
+            }
+            ss = ss2.x + ss2.y;
+        } else {
             const float2* xp = reinterpret_cast<const float2*>(sc + off);
             const float2 zt = make_float2(zthr, zthr);
             float2 ss2 = make_float2(0.0f, 0.0f);
@@ -1520,11 +1554,32 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
 
         // pass 1: 32-point FFT over n1 (z[lg + L*n1]); twiddle W_M^(lg*k1)
         fftreg2::fft_dif<32>(v);
+        if constexpr (TM) {
 #pragma unroll
-        for (int k1 = 1; k1 < 32; ++k1) {
-            const float2 w = s_tw1[(k1 - 1) * L + lg];
-            const int p = pos32(k1);
-            v[p] = fftreg2::cmul(v[p], w.x, w.y);
+            for (int kc = 0; kc < 4; kc += 2) {
+                uint32_t tr[16], tr2[16];
+                tmem_ld16_issue(tq + kSubTw1 + 16 * kc, tr);
+                tmem_ld16_issue(tq + kSubTw1 + 16 * kc + 16, tr2);
+                tmem_wait16(tr);
+                tmem_wait16(tr2);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int k1 = 8 * kc + u + 1;
+                    if (k1 < 32) {
+                        const int p = pos32(k1);
+                        const uint32_t c = (u < 8) ? tr[2 * (u & 7)] : tr2[2 * (u & 7)];
+                        const uint32_t sn = (u < 8) ? tr[2 * (u & 7) + 1] : tr2[2 * (u & 7) + 1];
+                        v[p] = fftreg2::cmul(v[p], __uint_as_float(c), __uint_as_float(sn));
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) {
+                const float2 w = s_tw1[(k1 - 1) * L + lg];
+                const int p = pos32(k1);
+                v[p] = fftreg2::cmul(v[p], w.x, w.y);
+            }
         }
         // transpose inside the group: lane lg then owns columns k1 = lg + L*c
 #pragma unroll
@@ -1565,9 +1620,17 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
         // real-FFT split, |X|^2, |X|, moments of |X| about the centres of the lane's two runs
         float2 P[16], S[16];
         float2 M0 = make_float2(0.f, 0.f), M1 = M0, M2 = M0;
+        uint32_t t2a[16], t2b[16];
+        if constexpr (TM) {
+            tmem_ld16_issue(tq + kSubTw2, t2a);
+            tmem_ld16_issue(tq + kSubTw2 + 16, t2b);
+            tmem_wait16(t2a);
+            tmem_wait16(t2b);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const float2 w = s_tw2[i * L + lg];
+            const float2 w = TM ? (i < 8 ? f2_of(t2a[2 * i], t2a[2 * i + 1]) : f2_of(t2b[2 * (i - 8)], t2b[2 * (i - 8) + 1]))
+                                : s_tw2[i * L + lg];
             const float2 za_ = v[i], zb_ = v[16 + i];
             const float2 e = __fadd2_rn(za_, make_float2(zb_.x, -zb_.y));
             const float2 d = __fadd2_rn(za_, make_float2(-zb_.x, zb_.y));
@@ -1671,12 +1734,22 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
             const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
             float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
                                             : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+            uint32_t col = tq + kSubMel;
             for (int r = 0; r < R; ++r) {
+                float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
+                if constexpr (TM) {
+                    const int n4 = ft.mel_steps[r];
+                    uint32_t st1[4];
+                    tmem_ld4(tq + kSubMeta + (r & ~3), st1);      // first taps of rounds 4*(r/4) .. +3
+                    const uint32_t start = (r & 2) ? ((r & 1) ? st1[3] : st1[2]) : ((r & 1) ? st1[1] : st1[0]);
+                    mel_steps_tm(n4, col, scp + start, a01, a23);
+                    col += 4 * n4;
+                } else {
                 const int n4 = s_meta[r];
                 const float4* wq = reinterpret_cast<const float4*>(s_melw + s_meta[R + r]) + lg;
                 const float* pq = scp + s_meta[2 * R + r * L + lg];
-                float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
                 mel_steps<L>(n4, wq, pq, a01, a23);
+                }
                 a01 = __fadd2_rn(a01, a23);
                 const float acc = a01.x + a01.y;
                 const int m = L * r + lg;
@@ -1706,26 +1779,32 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
         }
         __syncwarp();
     }
+    if constexpr (TM) tmem_tables_release(tbase, warp);
 }
 
-template <int L, bool HANN>
+template <int L, bool HANN, bool TM = false>
 static cudaError_t launch_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
                               cudaStream_t stream) {
     constexpr int NW = 16;
-    const int smem = sub_smem_bytes(ft, NW, L);
-    cudaError_t e = cudaFuncSetAttribute(frames_sub<L, NW, HANN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = sub_smem_bytes(ft, NW, L, TM);
+    cudaError_t e = cudaFuncSetAttribute(frames_sub<L, NW, HANN, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long units = (long long)a.B * ((a.T + SubGeom<L>::FW - 1) / SubGeom<L>::FW);
     if (units <= 0) return cudaSuccess;
     long long grid = (units + NW - 1) / NW;
     if (grid > num_sms) grid = num_sms;
-    frames_sub<L, NW, HANN><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
+    frames_sub<L, NW, HANN, TM><<<(unsigned)grid, NW * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
                               cudaStream_t stream) {
+    static const bool no_tm = [] { const char* e = getenv("HLMC_NO_TMEM"); return e && e[0] == '1'; }();
+    if (!no_tm && !a.no_tmem && ft.tmem_tab != nullptr && ft.n_groups <= 32) {
+        if (a.n_fft == 1024) return launch_sub<16, false, true>(a, d_tables, ft, num_sms, stream);
+        if (a.n_fft == 512) return launch_sub<8, false, true>(a, d_tables, ft, num_sms, stream);
+    }
     if (a.n_fft == 1024) return ft.hann ? launch_sub<16, true>(a, d_tables, ft, num_sms, stream)
                                         : launch_sub<16, false>(a, d_tables, ft, num_sms, stream);
     if (a.n_fft == 512) return ft.hann ? launch_sub<8, true>(a, d_tables, ft, num_sms, stream)

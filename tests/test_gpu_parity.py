@@ -617,7 +617,10 @@ def test_random_parameter_combinations(built, n, pitch_extra, kw):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(window="hamming"), dict(n_mels=40, n_mfcc=13), dict(n_mels=64, htk=True),
-                                dict(n_mels=256), dict(pad_mode="reflect", power=1.0), dict(win_length=1024)])
+                                dict(n_mels=256), dict(pad_mode="reflect", power=1.0), dict(win_length=1024),
+                                dict(n_fft=1024, hop_length=256), dict(n_fft=512, hop_length=128),
+                                dict(n_fft=1024, hop_length=300, window="hamming", n_mels=40, n_mfcc=13),
+                                dict(n_fft=512, hop_length=128, n_mels=256, pad_mode="edge")])
 def test_tensor_memory_tables_match_shared_memory_tables(built, kw):
     """The n_fft = 2048 kernel reads its per-lane tables (window, twiddles, banded mel weights, gather offsets) from
     Tensor Memory (tcgen05.ld); HLMC_PATH_FAST_SMEM_TABLES runs the same pipeline with the tables in shared memory.
@@ -645,6 +648,7 @@ def test_tensor_memory_tables_match_shared_memory_tables(built, kw):
                 keep = torch.tensor([0, 1, 4], device=d.device)
                 assert (d[keep] <= REL_TOL * scale[keep]).all(), (k, c, d.tolist(), scale.tolist())
     # the chroma variant (piptrack epilogue + power-spectrum stash) on both table paths
+    assert ex.uses_fast_path()
     if not kw:
         ex.set_path(0)
         ca = {k: v.clone() for k, v in ex.extract_device(yd, chroma=True).items()}
