@@ -606,6 +606,51 @@ int hlmc_plan_create(const hlmc_params* params, const double* window, const floa
             UP(d_fast4, blob)
             pl->fast4_ok = fast4_smem_bytes(ft) <= 227 * 1024;
             pl->fast_ok = pl->fast4_ok;
+            {   // the same tables per lane for Tensor Memory (frames_fast_4096<TM>), see k4Tm* in hlmc_internal.h
+                int total_steps = 0;
+                for (int par = 0; par < 2; ++par)
+                    for (int g = 0; g < ft.n_groups; ++g) total_steps += meta[par][g];
+                const int cols = k4TmMel + 4 * total_steps;
+                if (cols <= kTmAlloc) {
+                    std::vector<float> tm((size_t)32 * cols, 0.0f);
+                    int mel_col[2] = {0, 0};
+                    for (int l = 0; l < 32; ++l) {
+                        float* row = &tm[(size_t)l * cols];
+                        for (int k1 = 1; k1 < 32; ++k1) {
+                            row[k4TmTw1 + 2 * (k1 - 1)] = blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2];
+                            row[k4TmTw1 + 2 * (k1 - 1) + 1] = blob[ft.tw1 + ((k1 - 1) * 32 + l) * 2 + 1];
+                        }
+                        for (int j = 0; j < 32; ++j) {
+                            row[k4TmTw0 + 2 * j] = blob[ft.tw0 + (l + 32 * j) * 2];
+                            row[k4TmTw0 + 2 * j + 1] = blob[ft.tw0 + (l + 32 * j) * 2 + 1];
+                        }
+                        for (int par = 0; par < 2; ++par) {
+                            row[k4TmBase + 2 * par] = blob[ft.base + (32 * par + l) * 2];
+                            row[k4TmBase + 2 * par + 1] = blob[ft.base + (32 * par + l) * 2 + 1];
+                        }
+                        for (int c = 0; c < 4; ++c) row[k4TmHcs + c] = blob[ft.hann_cs + 4 * l + c];
+                        int pre = 0;
+                        for (int par = 0; par < 2; ++par) {
+                            mel_col[par] = k4TmMel + 4 * pre;
+                            for (int g = 0; g < ft.n_groups; ++g) {
+                                memcpy(&row[k4TmMeta + 4 * par + g], &meta[par][2 * kMaxMelGroups + 32 * g + l], 4);
+                                for (int st = 0; st < meta[par][g]; ++st)
+                                    for (int c = 0; c < 4; ++c)
+                                        row[k4TmMel + 4 * (pre + st) + c] =
+                                            melw[par][(size_t)meta[par][kMaxMelGroups + g] + ((size_t)st * 32 + l) * 4 + c];
+                                pre += meta[par][g];
+                            }
+                        }
+                    }
+                    UP(d_tmem_tab, tm)
+                    pl->ft4.tmem_tab = pl->d_tmem_tab;
+                    pl->ft4.tmem_cols = cols;
+                    for (int par = 0; par < 2; ++par) {
+                        pl->ft4.mel_col[par] = mel_col[par];
+                        for (int g = 0; g < ft.n_groups; ++g) pl->ft4.mel_steps[4 * par + g] = meta[par][g];
+                    }
+                }
+            }
         }
     }
     // register-FFT tables for n_fft = 1024 / 512: L = n_fft / 64 lanes per frame (frames_sub kernel)

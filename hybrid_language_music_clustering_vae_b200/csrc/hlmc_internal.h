@@ -40,6 +40,11 @@ struct Fast4Tables {
     int mel_w[2];     // per parity: banded weights of the de-interleaved filterbank columns
     int total;        // floats, multiple of 4
     int n_groups;     // <= 4 (n_mels <= 128)
+    // per-lane tables for Tensor Memory (TM variant; global memory, [32 lanes][tmem_cols] floats) or NULL
+    const float* tmem_tab;
+    int tmem_cols;
+    int mel_steps[8];     // float4 steps of (pass, group): [4 * pass + group]
+    int mel_col[2];       // first TMEM column of each pass's weights
 };
 
 // Column map of the Tensor Memory tables (floats per lane; see hlmc_kernels.cu "Tensor Memory as a per-lane table store")
@@ -55,6 +60,13 @@ constexpr int kSubTw1 = 64;     // 64: W_M^(lg*k1) as (cos, -sin), k1 = 1..31
 constexpr int kSubTw2 = 128;    // 32: -i*W_N^(16*lg + i), i = 0..15
 constexpr int kSubMeta = 160;   // 32: first tap of the lane's filter in each mel round (int32 bits)
 constexpr int kSubMel = 192;    // banded mel weights, float4 per step, round after round
+// ... and of frames_fast_4096's
+constexpr int k4TmTw1 = 0;      // 64: W_1024^(lane*k1) as (cos, -sin), k1 = 1..31
+constexpr int k4TmTw0 = 64;     // 64: W_2048^(lane + 32 j), j = 0..31 (the odd-bin pass's radix-2 twiddle)
+constexpr int k4TmBase = 128;   // 4: split-twiddle base of the lane for pass 0, pass 1
+constexpr int k4TmHcs = 132;    // 4: (cos, cos', sin, sin') of the lane's Hann phase
+constexpr int k4TmMeta = 136;   // 8: first gather tap of the lane's filter, [4 * pass + group]
+constexpr int k4TmMel = 144;    // banded mel weights: pass 0's groups, then pass 1's
 
 struct FrameArgs {
     const float* wave;      // (B, pitch)
@@ -131,7 +143,7 @@ cudaError_t launch_frames_fast(const FrameArgs& a, const float* d_tables, const 
                                int num_sms, cudaStream_t stream);
 cudaError_t launch_frames_fast4096(const FrameArgs& a, const float* d_tables, const Fast4Tables& ft, int num_sms,
                                    cudaStream_t stream);
-int fast4_smem_bytes(const Fast4Tables& ft);
+int fast4_smem_bytes(const Fast4Tables& ft, bool tm = false);
 cudaError_t launch_frames_sub(const FrameArgs& a, const float* d_tables, const FastTables& ft, int num_sms,
                               cudaStream_t stream);
 int sub_smem_bytes(const FastTables& ft, int nwarps, int L, bool tm = false);

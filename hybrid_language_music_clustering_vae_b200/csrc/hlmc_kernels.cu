@@ -208,11 +208,12 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
 __device__ __forceinline__ float2 f2_of(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 // CTA-wide: allocate the SM's Tensor Memory (all 512 columns: one CTA per SM), fill the four 32-lane quarters with
-// the per-lane tables ft.tmem_tab [32][ft.tmem_cols] (quarter warp%4 by its NW/4 warps, each a contiguous share of
+// the per-lane tables tmem_tab [32][tmem_cols] (quarter warp%4 by its NW/4 warps, each a contiguous share of
 // the columns, 4 loads in flight) and return the base address.  Ends with the fence half of a CTA barrier: the
 // caller's next __syncthreads() + tcgen05.fence::after_thread_sync publishes the tables.
 template <int NW>
-__device__ __forceinline__ uint32_t tmem_tables_setup(const FastTables& ft, uint32_t* s_taddr, int warp, int lane) {
+__device__ __forceinline__ uint32_t tmem_tables_setup(const float* __restrict__ tmem_tab, int tmem_cols, uint32_t* s_taddr,
+                                                      int warp, int lane) {
     static_assert(NW % 4 == 0, "a whole number of warps per TMEM quarter");
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_taddr)), "r"(kTmAlloc));
@@ -222,8 +223,8 @@ __device__ __forceinline__ uint32_t tmem_tables_setup(const FastTables& ft, uint
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = *s_taddr;
-    const float4* src = reinterpret_cast<const float4*>(ft.tmem_tab + (size_t)lane * ft.tmem_cols);
-    const int n4 = ft.tmem_cols / 4, per = (n4 + NW / 4 - 1) / (NW / 4);
+    const float4* src = reinterpret_cast<const float4*>(tmem_tab + (size_t)lane * tmem_cols);
+    const int n4 = tmem_cols / 4, per = (n4 + NW / 4 - 1) / (NW / 4);
     const int c0 = (warp >> 2) * per, c1 = min(n4, c0 + per);
     const uint32_t tqw = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
     for (int c = c0; c < c1; c += 4) {
@@ -647,7 +648,7 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         fence_mbar_init();
     }
     uint32_t tbase = 0;
-    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
+    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft.tmem_tab, ft.tmem_cols, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
     __syncthreads();
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
 
@@ -973,20 +974,44 @@ constexpr int k4Sev = k4T + 2180;                // pass-0 magnitudes, [lane][33
 constexpr int k4WarpFloats = k4Sev + 32 * 33;    // 5288
 constexpr int k4Warps = 8;
 
-int fast4_smem_bytes(const Fast4Tables& ft) { return (((2 * k4Warps + 3) & ~3) + ft.total + k4Warps * k4WarpFloats) * 4; }
+int fast4_smem_bytes(const Fast4Tables& ft, bool tm) {
+    return (((2 * k4Warps + 3 + (tm ? 4 : 0)) & ~3) + (tm ? 0 : ft.total) + k4Warps * k4WarpFloats) * 4;
+}
 
 // phases 1-5 of one 1024-point pass: v[j] = element lane + 32 j on entry; on exit v[i] / v[16+i] hold the
 // lane's low run k' = 16 lane + i and its partners (pass 0: 1024 - k', pass 1: 1023 - k').  `pass` is a
 // run-time value on purpose: both passes execute the SAME instructions (the kernel's code would otherwise
 // not fit the instruction cache; ncu showed 0.9 no-instruction stall cycles per issue with two copies).
+template <bool TM>
 __device__ __forceinline__ void fft1024_regroup(float2 (&v)[32], float2* __restrict__ sc2,
-                                                const float2* __restrict__ s_tw1, int lane, int pass, float2& e512) {
+                                                const float2* __restrict__ s_tw1, uint32_t tq, int lane, int pass, float2& e512) {
     fftreg2::fft_dif<32>(v);
+    if constexpr (TM) {
 #pragma unroll
-    for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 tw = s_tw1[(k1 - 1) * 32 + lane];
-        const int p = pos32(k1);
-        v[p] = fftreg2::cmul(v[p], tw.x, tw.y);
+        for (int kc = 0; kc < 4; kc += 2) {
+            uint32_t tr[16], tr2[16];
+            tmem_ld16_issue(tq + k4TmTw1 + 16 * kc, tr);
+            tmem_ld16_issue(tq + k4TmTw1 + 16 * kc + 16, tr2);
+            tmem_wait16(tr);
+            tmem_wait16(tr2);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int k1 = 8 * kc + u + 1;
+                if (k1 < 32) {
+                    const int p = pos32(k1);
+                    const uint32_t c = (u < 8) ? tr[2 * (u & 7)] : tr2[2 * (u & 7)];
+                    const uint32_t sn = (u < 8) ? tr[2 * (u & 7) + 1] : tr2[2 * (u & 7) + 1];
+                    v[p] = fftreg2::cmul(v[p], __uint_as_float(c), __uint_as_float(sn));
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+            const float2 tw = s_tw1[(k1 - 1) * 32 + lane];
+            const int p = pos32(k1);
+            v[p] = fftreg2::cmul(v[p], tw.x, tw.y);
+        }
     }
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) sc2[lane * 33 + k1] = v[pos32(k1)];
@@ -1037,42 +1062,67 @@ __device__ __forceinline__ void split_pass(const float2 (&v)[32], float2 tw_base
     }
 }
 
+// TM: every per-lane table (both twiddle sets, split bases, Hann phase, banded mel weights and first taps of both
+// passes) is read from Tensor Memory with tcgen05.ld instead of shared memory, as in frames_fast_2048.
+template <bool TM>
 __global__ void __launch_bounds__(k4Warps * 32, 1)
 frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fast4Tables ft) {
     extern __shared__ __align__(16) float smem[];
     constexpr int NW = k4Warps, NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem) + warp;
-    float* tab = smem + ((2 * NW + 3) & ~3);
+    float* tab = smem + ((2 * NW + 3 + (TM ? 4 : 0)) & ~3);
+    const int tab_total = TM ? 0 : ft.total;              // TM: no table is staged in shared memory
     const float2* s_tw1 = reinterpret_cast<const float2*>(tab + ft.tw1);
     const float2* s_tw0 = reinterpret_cast<const float2*>(tab + ft.tw0);
     const float2* s_base = reinterpret_cast<const float2*>(tab + ft.base);
     const float4* s_hcs = reinterpret_cast<const float4*>(tab + ft.hann_cs);
-    float* sc = tab + ft.total + warp * k4WarpFloats;       // landing zone; b after pass 0's first phase
+    float* sc = tab + tab_total + warp * k4WarpFloats;       // landing zone; b after pass 0's first phase
     float* scT = sc + k4T;                                  // transposes, then the pass's power spectrum
     float2* scT2 = reinterpret_cast<float2*>(scT);
     float* sev = sc + k4Sev;
 
-    for (int i = tid; i < ft.total / 4; i += NT)
+    for (int i = tid; i < tab_total / 4; i += NT)
         reinterpret_cast<float4*>(tab)[i] = __ldg(reinterpret_cast<const float4*>(g_tables) + i);
-    for (int i = tid; i < NW * k4WarpFloats; i += NT) (tab + ft.total)[i] = 0.0f;
+    for (int i = tid; i < NW * k4WarpFloats; i += NT) (tab + tab_total)[i] = 0.0f;
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    uint32_t tbase = 0;
+    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft.tmem_tab, ft.tmem_cols, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
     __syncthreads();
+    if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tq = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
 
     const long long total = (long long)a.B * a.T;
     const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
     const long long c0 = (long long)blockIdx.x * per_cta;
     const long long g1 = (c0 + per_cta < total) ? c0 + per_cta : total;
     const long long g0 = c0 + warp;
-    if (g0 >= g1) return;
+    if (!TM && g0 >= g1) return;                      // (TM: every warp stays for the TMEM deallocation)
     int b = (int)(g0 / a.T);
     int t = (int)(g0 - (long long)b * a.T);
     float clip_max = 0.0f;
     WarpState w{};
     w.sc = sc; w.sc2 = reinterpret_cast<float2*>(sc); w.mbar = mbar; w.parity = 0; w.lane = lane;
     const float zthr = a.zcr_thr;
-    const float4 hcs = s_hcs[lane];
+    float4 hcs;
+    if constexpr (TM) {
+        uint32_t h4[4];
+        tmem_ld4(tq + k4TmHcs, h4);
+        hcs = make_float4(__uint_as_float(h4[0]), __uint_as_float(h4[1]), __uint_as_float(h4[2]), __uint_as_float(h4[3]));
+    } else {
+        hcs = s_hcs[lane];
+    }
     const float2 hc = make_float2(hcs.x, hcs.y), hs = make_float2(hcs.z, hcs.w);
+    // split-twiddle bases of both passes and the first gather taps of the lane's (pass, group) filters
+    uint32_t tb4[4] = {0u, 0u, 0u, 0u}, mst[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if constexpr (TM) {
+        tmem_ld4(tq + k4TmBase, tb4);
+        uint32_t m0[4], m1[4];
+        tmem_ld4(tq + k4TmMeta, m0);
+        tmem_ld4(tq + k4TmMeta + 4, m1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { mst[i] = m0[i]; mst[4 + i] = m1[i]; }
+    }
 
     for (long long g = g0; g < g1; g += NW) {
         const float* clip = a.wave + (long long)b * a.pitch;
@@ -1166,17 +1216,33 @@ frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 // ---- odd bins: (z[m] - z[m+1024]) * W_2048^m
                 const float2* L2 = reinterpret_cast<const float2*>(sc + off);
 #pragma unroll
+                if constexpr (TM) {
+#pragma unroll
+                    for (int jc = 0; jc < 4; ++jc) {
+                        uint32_t tr[16];
+                        tmem_ld16_issue(tq + k4TmTw0 + 16 * jc, tr);
+                        float2 bq[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) bq[u] = L2[lane + 32 * (8 * jc + u)];
+                        tmem_wait16(tr);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            v[8 * jc + u] = fftreg2::cmul(bq[u], __uint_as_float(tr[2 * u]), __uint_as_float(tr[2 * u + 1]));
+                    }
+                } else {
+#pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float2 bq = L2[lane + 32 * j];
                     const float2 tw = s_tw0[lane + 32 * j];          // W_2048^m = (cos, -sin)
                     v[j] = fftreg2::cmul(bq, tw.x, tw.y);
                 }
+                }
             }
             __syncwarp();
 
             float2 e512, S[16], M0, M1, M2;
-            fft1024_regroup(v, scT2, s_tw1, lane, pass, e512);
-            split_pass(v, s_base[32 * pass + lane], P, S, M0, M1, M2);
+            fft1024_regroup<TM>(v, scT2, s_tw1, tq, lane, pass, e512);
+            split_pass(v, TM ? (pass ? f2_of(tb4[2], tb4[3]) : f2_of(tb4[0], tb4[1])) : s_base[32 * pass + lane], P, S, M0, M1, M2);
             if (pass == 0) {
                 A0 = M0; A1 = M1; A2 = M2;
                 p1024 = 4.0f * fmaf(e512.x, e512.x, e512.y * e512.y);      // bin 1024 (k' = 512) pairs with itself
@@ -1212,12 +1278,27 @@ frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fa
                 const size_t mstride = a.mel_frame_major ? 1 : (size_t)a.T;
                 float* outb = a.mel_frame_major ? a.mel_out + ((size_t)b * a.T + t) * a.n_mels
                                                 : a.mel_out + ((size_t)b * a.n_mels) * a.T + t;
+                uint32_t col = tq + (uint32_t)(pass ? ft.mel_col[1] : ft.mel_col[0]);
                 for (int gi = 0; gi < ft.n_groups; ++gi) {
+                    float2 a01 = make_float2(0.f, 0.f), a23 = a01;
+                    if constexpr (TM) {
+                        // (constant indices only: a run-time index into the kernel parameters costs a local copy of them)
+                        const int sel = 4 * pass + gi;
+                        uint32_t start = mst[0];
+                        int n4 = ft.mel_steps[0];
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) {
+                            start = (sel == i) ? mst[i] : start;
+                            n4 = (sel == i) ? ft.mel_steps[i] : n4;
+                        }
+                        mel_steps_tm(n4, col, scT + start, a01, a23);
+                        col += 4 * n4;
+                    } else {
                     const int n4 = meta[gi];
                     const float4* wp = reinterpret_cast<const float4*>(melw + meta[kMaxMelGroups + gi]) + lane;
                     const float* pp = scT + meta[2 * kMaxMelGroups + 32 * gi + lane];
-                    float2 a01 = make_float2(0.f, 0.f), a23 = a01;
                     mel_steps(n4, wp, pp, a01, a23);
+                    }
                     a01 = __fadd2_rn(a01, a23);
                     const float part = a01.x + a01.y;
                     if (pass == 0) {
@@ -1330,20 +1411,29 @@ frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         while (t >= a.T) { t -= a.T; ++b; }
         __syncwarp();
     }
+    if constexpr (TM) tmem_tables_release(tbase, warp);
 }
 
-cudaError_t launch_frames_fast4096(const FrameArgs& a, const float* d_tables, const Fast4Tables& ft, int num_sms,
-                                   cudaStream_t stream) {
-    const int smem = fast4_smem_bytes(ft);
-    cudaError_t e = cudaFuncSetAttribute(frames_fast_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <bool TM>
+static cudaError_t launch_fast4096_tm(const FrameArgs& a, const float* d_tables, const Fast4Tables& ft, int num_sms,
+                                      cudaStream_t stream) {
+    const int smem = fast4_smem_bytes(ft, TM);
+    cudaError_t e = cudaFuncSetAttribute(frames_fast_4096<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long frames = (long long)a.B * a.T;
     if (frames <= 0) return cudaSuccess;
     long long grid = (frames + k4Warps - 1) / k4Warps;
     if (grid > num_sms) grid = num_sms;
-    frames_fast_4096<<<(unsigned)grid, k4Warps * 32, smem, stream>>>(a, d_tables, ft);
+    frames_fast_4096<TM><<<(unsigned)grid, k4Warps * 32, smem, stream>>>(a, d_tables, ft);
     g_launches++;
     return cudaGetLastError();
+}
+
+cudaError_t launch_frames_fast4096(const FrameArgs& a, const float* d_tables, const Fast4Tables& ft, int num_sms,
+                                   cudaStream_t stream) {
+    static const bool no_tm = [] { const char* e = getenv("HLMC_NO_TMEM"); return e && e[0] == '1'; }();
+    if (!no_tm && !a.no_tmem && ft.tmem_tab != nullptr) return launch_fast4096_tm<true>(a, d_tables, ft, num_sms, stream);
+    return launch_fast4096_tm<false>(a, d_tables, ft, num_sms, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -1408,7 +1498,7 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
     for (int i = tid; i < NW * G::WB; i += NT) (tab + tab_total)[i] = 0.0f;
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     uint32_t tbase = 0;
-    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
+    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft.tmem_tab, ft.tmem_cols, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
     __syncthreads();
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tq = tbase + ((uint32_t)(32 * (warp & 3)) << 16);

@@ -620,7 +620,8 @@ def test_random_parameter_combinations(built, n, pitch_extra, kw):
                                 dict(n_mels=256), dict(pad_mode="reflect", power=1.0), dict(win_length=1024),
                                 dict(n_fft=1024, hop_length=256), dict(n_fft=512, hop_length=128),
                                 dict(n_fft=1024, hop_length=300, window="hamming", n_mels=40, n_mfcc=13),
-                                dict(n_fft=512, hop_length=128, n_mels=256, pad_mode="edge")])
+                                dict(n_fft=512, hop_length=128, n_mels=256, pad_mode="edge"),
+                                dict(n_fft=4096, hop_length=1024), dict(n_fft=4096, hop_length=1000, n_mels=64, pad_mode="reflect")])
 def test_tensor_memory_tables_match_shared_memory_tables(built, kw):
     """The n_fft = 2048 kernel reads its per-lane tables (window, twiddles, banded mel weights, gather offsets) from
     Tensor Memory (tcgen05.ld); HLMC_PATH_FAST_SMEM_TABLES runs the same pipeline with the tables in shared memory.
