@@ -1215,7 +1215,6 @@ frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fa
             } else {
                 // ---- odd bins: (z[m] - z[m+1024]) * W_2048^m
                 const float2* L2 = reinterpret_cast<const float2*>(sc + off);
-#pragma unroll
                 if constexpr (TM) {
 #pragma unroll
                     for (int jc = 0; jc < 4; ++jc) {
