@@ -71,6 +71,7 @@ struct hlmc_plan {
     // chroma_stft (built lazily): 100 filterbanks (one per tuning bin) + histogram edges
     float* d_chroma_fb = nullptr; double* d_edges = nullptr;
     int pip_klo = 0, pip_khi = 0, cand_per_frame = 0;
+    bool chroma_generic = false;                 // n_fft != 2048: candidates and projection through frames_generic
     // optional per-kernel timing (events recorded on the launching stream)
     int timing = 0;
     std::vector<cudaEvent_t> ev;      // triples: before frames, after frames, after db_dct
@@ -273,19 +274,26 @@ static void build_chroma_fb(int sr, int n_fft, double tuning, std::vector<float>
 
 static int ensure_chroma_tables(hlmc_plan* pl) {
     if (pl->d_chroma_fb) return HLMC_OK;
-    if (pl->p.n_fft != kFastNfft || !pl->fast_ok)
-        return fail(HLMC_ERR_UNSUPPORTED, "chroma_stft on device needs n_fft = 2048 (the register-FFT kernel)");
-    if (pl->p.power != 2.0f) return fail(HLMC_ERR_UNSUPPORTED, "chroma_stft on device needs a power=2 plan");
+    // n_fft = 2048 (the scripts' size): piptrack epilogue + power-spectrum stash of the register-FFT kernel.  Any
+    // other n_fft: two extra passes of the shared-memory FFT kernel (candidates, then the projection).
+    pl->chroma_generic = (pl->p.n_fft != kFastNfft || !pl->fast_ok);
+    if (!pl->chroma_generic && pl->p.power != 2.0f)
+        return fail(HLMC_ERR_UNSUPPORTED, "chroma_stft on device needs a power=2 plan");
     CK(cudaSetDevice(pl->device));       // callers may be on a fresh host thread whose current device is 0
     const int F = pl->F;
     // bins np.linspace(-0.5, 0.5, 101) of librosa.pitch_tuning (resolution 0.01)
     std::vector<double> edges(kTuningBins + 1);
     const double step = (0.5 - (-0.5)) / double(kTuningBins);
     for (int i = 0; i <= kTuningBins; ++i) edges[i] = (i == kTuningBins) ? 0.5 : i * step + (-0.5);
-    std::vector<float> all((size_t)kTuningBins * kChromaFbFloats, 0.0f), fb;
+    const size_t per_fb = pl->chroma_generic ? (size_t)kChroma * F : (size_t)kChromaFbFloats;
+    std::vector<float> all((size_t)kTuningBins * per_fb, 0.0f), fb;
     for (int tb = 0; tb < kTuningBins; ++tb) {
         build_chroma_fb(pl->p.sr, pl->p.n_fft, edges[tb], fb);
-        float* dst = &all[(size_t)tb * kChromaFbFloats];
+        float* dst = &all[(size_t)tb * per_fb];
+        if (pl->chroma_generic) {                      // dense (12, F) rows, as librosa.filters.chroma returns them
+            memcpy(dst, fb.data(), per_fb * 4);
+            continue;
+        }
         for (int c = 0; c < kChroma; ++c) {
             for (int l = 0; l < 32; ++l)
                 for (int j = 0; j < 32; ++j) {
@@ -899,7 +907,7 @@ int64_t hlmc_chroma_workspace_bytes(hlmc_plan* plan, int64_t B, int64_t n) {
     if (rc != HLMC_OK) return rc;
     const int64_t T = hlmc_num_frames(&plan->p, n);
     if (T < 0) return T;
-    return (int64_t)(chroma_ws_core(plan, B, T) + (size_t)B * T * kStashFloats * 4);
+    return (int64_t)(chroma_ws_core(plan, B, T) + (plan->chroma_generic ? 0 : (size_t)B * T * kStashFloats * 4));
 }
 
 // d_pooled with d_logmel == NULL selects the fused path: dB, DCT and time pooling in one kernel, the
@@ -959,7 +967,7 @@ static int extract_device_body(hlmc_plan* plan, const float* d_wave, int64_t B, 
     if (d_chroma) {
         rc = ensure_chroma_tables(plan);
         if (rc != HLMC_OK) return rc;
-        if (plan->force_generic) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs the register-FFT kernel");
+        if (plan->force_generic && !plan->chroma_generic) return fail(HLMC_ERR_UNSUPPORTED, "chroma needs the register-FFT kernel");
         const size_t core = chroma_ws_core(plan, B, T);
         if (!d_work || work_bytes < (int64_t)core) return fail(HLMC_ERR_PARAM, "chroma workspace too small");
         char* wsp = static_cast<char*>(d_work);
@@ -967,9 +975,10 @@ static int extract_device_body(hlmc_plan* plan, const float* d_wave, int64_t B, 
         tuning_idx = reinterpret_cast<int*>(wsp + align256((size_t)B * T * 4));
         cand = reinterpret_cast<float2*>(wsp + align256((size_t)B * T * 4) + align256((size_t)B * 4));
         cand_cap = plan->cand_per_frame;
-        if (work_bytes >= (int64_t)(core + (size_t)B * T * kStashFloats * 4))
+        if (!plan->chroma_generic && work_bytes >= (int64_t)(core + (size_t)B * T * kStashFloats * 4))
             pstash = reinterpret_cast<float*>(wsp + core);
     }
+    const bool cgen = d_chroma && plan->chroma_generic;
     cudaEvent_t (&ev3)[3] = own.ev;
     if (plan->timing) {
         if (plan->ev.size() >= 3 * 1024) { rc = fold_timing(plan); if (rc != HLMC_OK) return rc; }
@@ -984,7 +993,7 @@ static int extract_device_body(hlmc_plan* plan, const float* d_wave, int64_t B, 
         d_melscr = own.melscr;
     }
     rc = run_frames(plan, d_wave, B, n, pitch, (int)T, d_melscr, d_stats, d_status, d_clipmax, nullptr, st,
-                    cand, cand_count, cand_cap, 1, pstash);
+                    cgen ? nullptr : cand, cgen ? nullptr : cand_count, cgen ? 0 : cand_cap, 1, pstash);
     if (rc != HLMC_OK) return rc;
     if (plan->timing) CK(cudaEventRecord(ev3[1], st));
     DbArgs d{};
@@ -993,6 +1002,18 @@ static int extract_device_body(hlmc_plan* plan, const float* d_wave, int64_t B, 
     d.ncp = plan->ncp; d.T = (int)T; d.ref_mode = plan->p.ref_mode; d.ref_value = plan->p.ref_value;
     d.amin = plan->p.amin; d.top_db = plan->p.top_db;
     auto run_chroma = [&]() -> int {
+        if (cgen) {
+            // any n_fft: candidates from one pass of the shared-memory FFT kernel, the projection from a second
+            GenericTables gt{plan->d_win, plan->d_twm, plan->d_tws, plan->d_mel_lo, plan->d_mel_len, plan->d_mel_off, plan->d_mel_w};
+            FrameArgs a = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
+            a.cand = cand; a.cand_count = cand_count; a.cand_cap = cand_cap;
+            CK(launch_frames_generic(a, gt, st));
+            CK(launch_tuning(cand, cand_count, (int)T, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
+            FrameArgs a2 = make_frame_args(plan, d_wave, B, n, pitch, (int)T);
+            a2.chroma_out = d_chroma; a2.chroma_fb = plan->d_chroma_fb; a2.chroma_tidx = tuning_idx;
+            CK(launch_frames_generic(a2, gt, st));
+            return HLMC_OK;
+        }
         CK(launch_tuning(cand, cand_count, (int)T, cand_cap, B, plan->d_edges, d_tuning, tuning_idx, st));
         ChromaArgs ca{tuning_idx, plan->d_chroma_fb, d_chroma};
         if (pstash) {

@@ -95,6 +95,11 @@ struct FrameArgs {
     // (B, T, kStashFloats), each lane's 32 bins in its register order [lane][32], then bin 512
     float* pstash;
     int no_tmem;            // 1: keep the n_fft 2048 kernel's tables in shared memory (hlmc_plan_set_path, tests)
+    // chroma_stft for any n_fft (frames_generic only): projection of the frame's power spectrum onto the clip's
+    // tuned filterbank, chroma_out (B, 12, T); chroma_fb is (100, 12, 1 + n_fft/2) dense, chroma_tidx (B)
+    float* chroma_out;
+    const float* chroma_fb;
+    const int* chroma_tidx;
 };
 constexpr int kStashFloats = 32 * 32 + 4;
 

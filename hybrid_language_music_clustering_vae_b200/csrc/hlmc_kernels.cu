@@ -2318,6 +2318,50 @@ frames_generic(const FrameArgs a, const GenericTables gt, int logM) {
         }
     }
     __syncwarp();
+    // ---- librosa.piptrack candidates for chroma_stft's tuning estimate (any n_fft; same arithmetic as the
+    //      epilogue of frames_fast_2048<*, true>)
+    if (a.cand != nullptr) {
+        float pmax = 0.0f;
+        for (int k = lane; k < F; k += 32) pmax = fmaxf(pmax, Pb[k]);
+        pmax = warp_max(pmax);
+        const float ref = a.pip_threshold * pmax;
+        float2* slots = a.cand + ((size_t)b * a.T + t) * a.cand_cap;
+        int base = 0;
+        for (int k0 = a.pip_klo; k0 < a.pip_khi; k0 += 32) {
+            const int k = k0 + lane;
+            const bool in = k < a.pip_khi;
+            const int kk = in ? k : a.pip_klo;
+            const float pm1 = Pb[kk - 1], p0 = Pb[kk], pp1 = Pb[kk + 1];
+            const float xm = (pm1 > ref) ? pm1 : 0.0f, x0 = (p0 > ref) ? p0 : 0.0f, xp = (pp1 > ref) ? pp1 : 0.0f;
+            const bool peak = in && (x0 > xm) && (x0 >= xp);
+            const unsigned bal = __ballot_sync(FULL, peak);
+            if (peak) {
+                const float avg = (pp1 - pm1) * 0.5f;
+                const float aa = (pp1 + pm1) - 2.0f * p0;
+                const float shift = (fabsf(avg) >= fabsf(aa)) ? 0.0f : -avg / aa;
+                const float pitch = (float(k) + shift) * a.binhz;
+                const float mag = p0 + (0.5f * avg) * shift;
+                const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                if (slot < a.cand_cap) slots[slot] = make_float2(pitch, mag);
+            }
+            base += __popc(bal);
+        }
+        if (lane == 0) a.cand_count[(size_t)b * a.T + t] = min(base, a.cand_cap);
+    }
+    // ---- chroma_stft: the clip's tuned filterbank applied to this frame's power spectrum, util.normalize(norm=inf)
+    if (a.chroma_out != nullptr) {
+        const float* fb = a.chroma_fb + (size_t)a.chroma_tidx[b] * kChroma * F;
+        float mine = 0.0f;
+        for (int c = 0; c < kChroma; ++c) {
+            float acc = 0.0f;
+            for (int k = lane; k < F; k += 32) acc = fmaf(__ldg(fb + (size_t)c * F + k), Pb[k], acc);
+            acc = warp_sum(acc);
+            if (lane == c) mine = acc;
+        }
+        const float mx = warp_max(fabsf(mine));        // lanes >= 12 hold 0
+        const float inv = (mx < 1.17549435e-38f) ? 1.0f : 1.0f / mx;
+        if (lane < kChroma) a.chroma_out[((size_t)b * kChroma + lane) * a.T + t] = mine * inv;
+    }
     for (int k = lane; k < F; k += 32) {
         const float s = sqrtf(Pb[k]);
         s0 += s;

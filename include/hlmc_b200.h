@@ -160,9 +160,10 @@ int hlmc_graph_launch(hlmc_graph *graph, void *stream);
 void hlmc_graph_destroy(hlmc_graph *graph);
 
 /* The same plus librosa.feature.chroma_stft ([R] src/1_preprocessing.py:96-101,
- * src/1_preprocessing_advanced.py:139-141).  SCOPE: plans with n_fft = 2048 and power = 2 only - the one
- * configuration both scripts use; any other n_fft returns HLMC_ERR_UNSUPPORTED (chroma for n_fft 512 / 1024 /
- * 4096 is OUT of this library: the piptrack epilogue and the power-spectrum stash live in the 2048 kernel):
+ * src/1_preprocessing_advanced.py:139-141).  n_fft = 2048 (the one configuration both scripts use; needs a
+ * power = 2 plan) takes the piptrack epilogue and the power-spectrum stash of the register-FFT kernel; any other
+ * power-of-two n_fft gets the same chroma from two extra passes of the shared-memory FFT kernel (candidates,
+ * then the projection): correct for every n_fft, fast for the scripts' one:
  *   d_chroma : (B, 12, T) float32, each frame divided by its largest chroma bin, or NULL
  *   d_tuning : (B) float32, the per-clip librosa.estimate_tuning result, or NULL
  *   d_work   : hlmc_chroma_workspace_bytes(plan, B, n) bytes of device scratch

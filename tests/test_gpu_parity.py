@@ -424,8 +424,40 @@ def test_chroma_stft_and_tuning_on_device(built):
     assert np.array_equal(hp2["pooled"][:, 336:], po[:, 336:])          # statistics + chroma columns: same arithmetic
     c1 = hl.feature.chroma_stft(y=y[3], sr=SR, n_fft=2048, hop_length=512)
     assert c1.shape == (12, 130) and np.array_equal(c1, ch[3])
-    with pytest.raises(hl.UnsupportedError):
-        hl.FeatureExtractor(n_fft=1024).extract_device(torch.zeros(1, 8000, device="cuda"), chroma=True)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(1024, 256), (4096, 1024), (512, 128), (256, 100)])
+def test_chroma_stft_for_other_n_fft(built, n_fft, hop):
+    """chroma_stft + the tuning estimate for the n_fft values the scripts do not use (BASELINE configs[4] sweeps them):
+    candidates and projection come from the shared-memory FFT kernel; same tolerances as the n_fft = 2048 path."""
+    import torch
+
+    hl = built
+    y = hl.synth.synth_batch(6, 30000, seed=n_fft + 3)
+    ex = hl.FeatureExtractor(n_fft=n_fft, hop_length=hop, n_mfcc=13)
+    out = ex.extract_device(torch.from_numpy(y).cuda(), chroma=True, pooled=True)
+    ch, tu = out["chroma"].cpu().numpy(), out["tuning"].cpu().numpy()
+    ties = 0
+    for b in range(len(y)):
+        S = np.abs(orc.stft(y[b], n_fft=n_fft, hop_length=hop)) ** 2
+        t_or = orc.estimate_tuning(S=S, sr=SR, n_fft=n_fft, bins_per_octave=12)
+        if abs(tu[b] - t_or) > 1e-6:          # only an exact tie of the oracle's own histogram may move the arg-max
+            p_, m_ = orc.piptrack(S=S, sr=SR, n_fft=n_fft)
+            sel = p_[(m_ >= np.median(m_[p_ > 0])) & (p_ > 0)]
+            res = np.mod(12 * np.log2(sel / 27.5), 1.0)
+            res[res >= 0.5] -= 1.0
+            counts, _edges = np.histogram(res, np.linspace(-0.5, 0.5, 101))
+            assert counts[int(round((tu[b] + 0.5) * 100))] == counts.max(), (b, tu[b], t_or)
+            ties += 1
+        want = orc.chroma_stft(y=y[b], sr=SR, n_fft=n_fft, hop_length=hop, tuning=float(tu[b]))
+        assert ch[b].shape == want.shape == (12, 1 + 30000 // hop)
+        assert np.abs(ch[b] - want).max() <= 1e-4, (b, np.abs(ch[b] - want).max())
+    assert ties <= 1
+    # the pooled chroma columns are the mean / std of exactly these rows
+    po = out["pooled"].cpu().numpy()
+    assert np.allclose(po[:, -24:-12], ch.mean(axis=2), atol=1e-5) and np.allclose(po[:, -12:], ch.std(axis=2), atol=1e-5)
+    c1 = hl.feature.chroma_stft(y=y[2], sr=SR, n_fft=n_fft, hop_length=hop)
+    assert np.array_equal(c1, ch[2])
 
 
 def test_empty_and_degenerate_batches(built):
