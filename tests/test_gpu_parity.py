@@ -689,3 +689,30 @@ def test_tensor_memory_tables_match_shared_memory_tables(built, kw):
         cb = ex.extract_device(yd, chroma=True)
         assert torch.equal(ca["tuning"], cb["tuning"])
         assert (ca["chroma"] - cb["chroma"]).abs().max().item() <= 1e-5
+
+
+def test_caller_supplied_filterbanks(built):
+    """hlmc_plan_create(mel_basis=...): a caller's own filterbank replaces librosa.filters.mel.  A banded one (wider
+    triangles than Slaney's) still fits the Tensor-Memory tables or the shared-memory ones; a fully dense one fits
+    neither and runs on the shared-memory FFT kernel.  Both must equal basis @ |STFT|^2 of the oracle."""
+    import torch
+
+    hl = built
+    rng = np.random.default_rng(12)
+    y = hl.synth.synth_batch(4, 20000, seed=8)
+    F = 1025
+    tri = np.zeros((24, F), np.float32)
+    for m in range(24):                                  # overlapping triangles 120 bins wide
+        c, hw = 40 * m + 30, 60
+        k = np.arange(max(0, c - hw), min(F, c + hw + 1))
+        tri[m, k] = 1.0 - np.abs(k - c) / float(hw + 1)
+    dense = rng.uniform(0.0, 1.0, (16, F)).astype(np.float32)
+    for name, basis in (("banded", tri), ("dense", dense)):
+        ex = hl.FeatureExtractor(n_mels=basis.shape[0], n_mfcc=8, ref=np.max, mel_basis=basis)
+        assert np.array_equal(ex.mel_basis(), basis)
+        out = ex.extract_device(torch.from_numpy(y).cuda())
+        lm = out["logmel"].cpu().numpy()
+        for b in range(len(y)):
+            S = np.abs(orc.stft(y[b])) ** 2
+            want = orc.power_to_db(basis.astype(np.float64) @ S, ref=np.max)
+            assert np.abs(lm[b] - want).max() <= LOGMEL_TOL_DB, (name, b, np.abs(lm[b] - want).max())
