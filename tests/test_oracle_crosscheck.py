@@ -107,3 +107,21 @@ def test_spectral_centroid_matches_torchaudio():
                                            hop_length=512, win_length=2048).numpy()
     got = orc.spectral_centroid(y=y, sr=SR, pad_mode="reflect")[0]      # torchaudio's spectrogram pads by reflection
     assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (1024, 256), (512, 100)])
+def test_oracle_stft_matches_scipy_signal(n_fft, hop):
+    """A third party's STFT: scipy.signal.stft with the periodic Hann window, zero 'boundary' extension of n_fft/2
+    samples on both sides (librosa's center=True, pad_mode="constant") and no trailing padding frames the same
+    samples at the same hops; its 'spectrum' scaling divides by sum(window)."""
+    from scipy.signal import get_window, stft
+
+    y = _clip(7, n=3 * n_fft + 123).astype(np.float64)
+    win = get_window("hann", n_fft, fftbins=True)
+    _f, _t, Z = stft(y, fs=SR, window=win, nperseg=n_fft, noverlap=n_fft - hop, nfft=n_fft, boundary="zeros",
+                     padded=False, return_onesided=True, scaling="spectrum")
+    D = orc.stft(y.astype(np.float32), n_fft=n_fft, hop_length=hop, pad_mode="constant")
+    T = min(D.shape[1], Z.shape[1])           # scipy drops a trailing partial hop, librosa keeps 1 + n // hop frames
+    assert T >= D.shape[1] - 1
+    got, want = D[:, :T], Z[:, :T] * win.sum()
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
