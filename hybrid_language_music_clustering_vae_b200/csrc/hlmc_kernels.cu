@@ -668,7 +668,8 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     w.sc = sc; w.sc2 = sc2; w.mbar = mbar; w.parity = 0;
     w.s_win = s_win; w.s_tw1 = s_tw1; w.s_tw2 = s_tw2; w.lane = lane;
     w.s_hcs = reinterpret_cast<const float4*>(tab + ft.hann_cs);
-    w.tq = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    // (REDUX leaves its result in a uniform register: the tcgen05.ld addresses derived from it need no R2UR)
+    w.tq = __reduce_or_sync(FULL, tbase + ((uint32_t)(32 * (warp & 3)) << 16));
     w.pending = false; w.pend_off = 0;
     // per-lane bases of the regroup buffer, layout p(k) = k + k/16 in float2 units: every
     // access is base + immediate and conflict-free (17 is odd)
@@ -1090,7 +1091,7 @@ frames_fast_4096(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     if constexpr (TM) tbase = tmem_tables_setup<NW>(ft.tmem_tab, ft.tmem_cols, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
     __syncthreads();
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tq = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    const uint32_t tq = __reduce_or_sync(FULL, tbase + ((uint32_t)(32 * (warp & 3)) << 16));   // uniform register: no R2UR per tcgen05.ld
 
     const long long total = (long long)a.B * a.T;
     const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
@@ -1500,7 +1501,7 @@ frames_sub(const FrameArgs a, const float* __restrict__ g_tables, const FastTabl
     if constexpr (TM) tbase = tmem_tables_setup<NW>(ft.tmem_tab, ft.tmem_cols, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
     __syncthreads();
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tq = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    const uint32_t tq = __reduce_or_sync(FULL, tbase + ((uint32_t)(32 * (warp & 3)) << 16));   // uniform register: no R2UR per tcgen05.ld
 
     // units of FW consecutive frames; a CTA owns a contiguous run of units, warps take them round-robin
     const int units_per_clip = (a.T + G::FW - 1) / G::FW;
