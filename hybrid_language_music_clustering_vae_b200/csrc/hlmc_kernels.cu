@@ -647,11 +647,6 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
         mbar_init(mbar, 1);
         fence_mbar_init();
     }
-    uint32_t tbase = 0;
-    if constexpr (TM) tbase = tmem_tables_setup<NW>(ft.tmem_tab, ft.tmem_cols, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
-    __syncthreads();
-    if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
-
     // ---- frame assignment: the CTA owns a contiguous run of (clip, frame) pairs and its NW warps
     //      take them round-robin, so at any moment one SM works on NW neighbouring frames of one
     //      clip (their 75 %-overlapping samples are hot in L2) and the whole GPU on ~148 clips
@@ -660,17 +655,30 @@ frames_fast_2048(const FrameArgs a, const float* __restrict__ g_tables, const Fa
     const long long c0 = (long long)blockIdx.x * per_cta;
     const long long g1 = (c0 + per_cta < total) ? c0 + per_cta : total;
     const long long g0 = c0 + warp;
-    if (!TM && g0 >= g1) return;                 // (TM kernels: every warp stays for the TMEM deallocation)
     int b = (int)(g0 / a.T);
     int t = (int)(g0 - (long long)b * a.T);
-    float clip_max = 0.0f;
     WarpState w;
     w.sc = sc; w.sc2 = sc2; w.mbar = mbar; w.parity = 0;
     w.s_win = s_win; w.s_tw1 = s_tw1; w.s_tw2 = s_tw2; w.lane = lane;
     w.s_hcs = reinterpret_cast<const float4*>(tab + ft.hann_cs);
+    w.pending = false; w.pend_off = 0;
+    uint32_t tbase = 0;
+    if constexpr (TM) {
+        // the first frame's copy flies while the Tensor Memory tables are filled (what a one-clip call waits for)
+        __syncthreads();                         // the landing zones are zeroed, the mbarriers initialised
+        if (g0 < g1) {
+            const int sh = issue_frame_tma(a, w, sc + kLandOff, a.wave + (long long)b * a.pitch, t);
+            w.pending = sh >= 0;
+            w.pend_off = sh;
+        }
+        tbase = tmem_tables_setup<NW>(ft.tmem_tab, ft.tmem_cols, reinterpret_cast<uint32_t*>(smem + 2 * NW), warp, lane);
+    }
+    __syncthreads();
+    if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
+    if (!TM && g0 >= g1) return;                 // (TM kernels: every warp stays for the TMEM deallocation)
+    float clip_max = 0.0f;
     // (REDUX leaves its result in a uniform register: the tcgen05.ld addresses derived from it need no R2UR)
     w.tq = __reduce_or_sync(FULL, tbase + ((uint32_t)(32 * (warp & 3)) << 16));
-    w.pending = false; w.pend_off = 0;
     // per-lane bases of the regroup buffer, layout p(k) = k + k/16 in float2 units: every
     // access is base + immediate and conflict-free (17 is odd)
     w.zw_base = lane + (lane >> 4);              // write: k = lane + 32*k2 -> zw_base + 34*k2
@@ -2591,6 +2599,110 @@ __global__ void __launch_bounds__(kDbThreads, (NC <= 32) ? 4 : (NC <= 40) ? 3 : 
     }
 }
 
+// ---------------------------------------------------------------------------
+// db_dct_small: the same power_to_db + DCT-II for SMALL batches (the reference's per-file loop: one clip = 130 frames).
+// db_dct gives a thread two whole frames - 128 mel bands, 16 dependent load -> dB -> 320-FMA rounds - so a single clip
+// is one CTA running a 20 us serial chain (longer than the frames kernel).  Here four lanes share a frame: per round
+// of 4 mirrored band pairs lane q loads and converts pair q (and writes its two log-mel values), the four (s, d)
+// pairs meet in shuffles, and every lane accumulates its own quarter of the DCT coefficients over ALL bands - in
+// db_dct's order, from db_dct's folded table, so log-mel AND MFCC are bitwise what db_dct writes whatever the batch
+// size.  A warp carries 8 frames, a CTA 32: a clip spreads over 5 CTAs of short chains.  Stores are 32-byte pieces
+// (8 frames of one band), which is why large batches stay on db_dct.
+// ---------------------------------------------------------------------------
+constexpr int kDbsThreads = 128;
+
+template <int NC>
+__global__ void __launch_bounds__(kDbsThreads) db_dct_small(const DbArgs a) {
+    extern __shared__ __align__(16) float sD[];         // db_dct's folded table: sD[n][j], j < H: coefficient 2j, else 2(j-H)+1
+    constexpr int H = NC / 2, HQ = H / 4;                // NC is a multiple of 8: every lane owns HQ even and HQ odd coefficients
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = lane >> 2, q = lane & 3, fbase = lane & ~3;
+    const int half = a.n_mels >> 1;
+    {
+        const int rows = (a.n_mels + 1) >> 1;
+        for (int i = tid; i < rows * NC; i += kDbsThreads) {
+            const int n = i / NC, j = i - n * NC;
+            const int c = (j < H) ? 2 * j : 2 * (j - H) + 1;
+            sD[i] = a.dct_t[n * NC + c];
+        }
+        __syncthreads();
+    }
+    const long long total = (long long)a.B * a.T;
+    long long G = ((long long)blockIdx.x * (kDbsThreads / 32) + warp) * 8 + f;
+    const bool live = G < total;
+    if (!live) G = total - 1;
+    const int b = (int)(G / a.T), t = (int)(G - (long long)b * a.T);
+    const float pmax = __uint_as_float(a.clipmax[b]);
+    const float maxa = db10(fmaxf(a.amin, pmax));
+    const float ref_db = (a.ref_mode == 1) ? maxa : db10(fmaxf(a.amin, fabsf(a.ref_value)));
+    const float floor_db = (a.top_db >= 0.0f) ? (maxa - ref_db) - a.top_db : -CUDART_INF_F;
+    const float floor_m = db10(fmaxf(1e-10f, pmax)) - 80.0f;   // librosa.feature.mfcc: ref = 1, amin = 1e-10, top_db = 80
+    const bool same_amin = (a.amin == 1e-10f);
+    float* col = a.mel + (size_t)b * a.n_mels * a.T + t;
+    const float* row = a.mel_in ? a.mel_in + ((size_t)b * a.T + t) * a.n_mels : nullptr;
+    auto fetch = [&](int m) -> float { return row ? __ldg(row + m) : col[(size_t)m * a.T]; };
+    auto to_db = [&](float p, int m) -> float {
+        const float adb = db10(fmaxf(a.amin, p));
+        if (live) col[(size_t)m * a.T] = fmaxf(adb - ref_db, floor_db);
+        const float x = same_amin ? adb : db10(fmaxf(1e-10f, p));
+        return fmaxf(x, floor_m);
+    };
+    float ae[HQ], ao[HQ];                               // coefficients 2 (HQ q + i) and 2 (HQ q + i) + 1
+#pragma unroll
+    for (int i = 0; i < HQ; ++i) { ae[i] = 0.0f; ao[i] = 0.0f; }
+    for (int n0 = 0; n0 < half; n0 += 4) {
+        const int n = n0 + q;
+        float s = 0.0f, d = 0.0f;
+        if (n < half) {                                 // this lane's mirrored pair of the round
+            const float xl = to_db(fetch(n), n), xh = to_db(fetch(a.n_mels - 1 - n), a.n_mels - 1 - n);
+            s = xl + xh; d = xl - xh;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                   // all four pairs, in db_dct's order
+            const float sj = __shfl_sync(FULL, s, fbase + j), dj = __shfl_sync(FULL, d, fbase + j);
+            if (n0 + j < half) {
+                const float* dr = sD + (n0 + j) * NC + HQ * q;
+#pragma unroll
+                for (int i = 0; i < HQ; ++i) {
+                    ae[i] = fmaf(dr[i], sj, ae[i]);
+                    ao[i] = fmaf(dr[H + i], dj, ao[i]);
+                }
+            }
+        }
+    }
+    if (a.n_mels & 1) {                                 // middle row: odd coefficients vanish there
+        float x = 0.0f;
+        if (q == 0) x = to_db(fetch(half), half);
+        x = __shfl_sync(FULL, x, fbase);
+#pragma unroll
+        for (int i = 0; i < HQ; ++i) ae[i] = fmaf(sD[half * NC + HQ * q + i], x, ae[i]);
+    }
+    if (live) {
+        float* mo = a.mfcc + (size_t)b * a.n_mfcc * a.T + t;
+#pragma unroll
+        for (int i = 0; i < HQ; ++i) {
+            const int ce = 2 * (HQ * q + i);
+            if (ce < a.n_mfcc) mo[(size_t)ce * a.T] = ae[i];
+            if (ce + 1 < a.n_mfcc) mo[(size_t)(ce + 1) * a.T] = ao[i];
+        }
+    }
+}
+
+template <int NC>
+static cudaError_t launch_db_small_nc(const DbArgs& a, cudaStream_t stream) {
+    const long long frames = (long long)a.B * a.T;
+    if (frames <= 0) return cudaSuccess;
+    const int smem = ((a.n_mels + 1) / 2) * NC * 4;   // folded DCT table
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(db_dct_small<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    const long long per_block = (kDbsThreads / 32) * 8;
+    db_dct_small<NC><<<(unsigned)((frames + per_block - 1) / per_block), kDbsThreads, smem, stream>>>(a);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 template <int NC>
 static cudaError_t launch_db_nc(const DbArgs& a, cudaStream_t stream) {
     const long long frames = (long long)a.B * a.T;
@@ -2839,7 +2951,21 @@ cudaError_t launch_db_pool(const DbArgs& a, const PoolArgs& pa, int num_sms, cud
     }
 }
 
+// frames below which the four-lanes-per-frame kernel is faster (measured crossover, tools/gpu_small_batch.py)
+constexpr long long kDbSmallFrames = 24000;
+
 cudaError_t launch_db_dct(const DbArgs& a, cudaStream_t stream) {
+    static const long long small_frames = [] { const char* e = getenv("HLMC_DB_SMALL"); return e ? atoll(e) : kDbSmallFrames; }();
+    if ((long long)a.B * a.T <= small_frames && a.mfcc != nullptr && a.n_mfcc > 0) {
+        switch (a.ncp) {
+            case 8: return launch_db_small_nc<8>(a, stream);
+            case 16: return launch_db_small_nc<16>(a, stream);
+            case 24: return launch_db_small_nc<24>(a, stream);
+            case 32: return launch_db_small_nc<32>(a, stream);
+            case 40: return launch_db_small_nc<40>(a, stream);
+            default: break;
+        }
+    }
     if (a.mfcc == nullptr || a.n_mfcc <= 0) return launch_db_nc<0>(a, stream);
     switch (a.ncp) {
         case 8: return launch_db_nc<8>(a, stream);

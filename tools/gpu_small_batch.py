@@ -11,9 +11,9 @@ def timeit(fn, reps, warm=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 ex = hl.FeatureExtractor(n_mfcc=40, ref=np.max)
-for path in (0, 2):
+for path in (0,):
     ex.set_path(path)
-    for B in (1, 8, 64, 128, 512):
+    for B in (1, 8, 64, 128, 256, 512):
         y = torch.randn((B, 66150), device="cuda") * 0.1
         out = ex.extract_device(y)
         ms = timeit(lambda: ex.extract_device(y, out=out), 50)
