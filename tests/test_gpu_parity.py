@@ -716,3 +716,20 @@ def test_caller_supplied_filterbanks(built):
             S = np.abs(orc.stft(y[b])) ** 2
             want = orc.power_to_db(basis.astype(np.float64) @ S, ref=np.max)
             assert np.abs(lm[b] - want).max() <= LOGMEL_TOL_DB, (name, b, np.abs(lm[b] - want).max())
+
+
+def test_small_batch_db_kernel_is_bitwise_the_large_batch_one(built):
+    """Batches up to 24,000 frames run db_dct_small (four lanes per frame), larger ones db_dct (a thread per two
+    frames): same table, same summation order - log-mel and MFCC must not depend on the batch size, bit for bit."""
+    import torch
+
+    hl = built
+    for kw in (dict(n_mfcc=40), dict(n_mfcc=13, n_mels=40), dict(n_mfcc=20, n_mels=127, ref=1.0, top_db=None)):
+        ref = kw.pop("ref", np.max)
+        top_db = kw.pop("top_db", 80.0)
+        ex = hl.FeatureExtractor(ref=ref, top_db=top_db, **kw)
+        y = torch.from_numpy(hl.synth.synth_batch(8, 22050, seed=90)).cuda()      # 44 frames per clip
+        small = {k: v.clone() for k, v in ex.extract_device(y).items()}            # 352 frames
+        big = ex.extract_device(torch.cat([y] * 80, dim=0))                         # 28,160 frames
+        for k in ("logmel", "mfcc", "stats"):
+            assert torch.equal(big[k][:8], small[k]) and torch.equal(big[k][-8:], small[k]), (kw, k)
